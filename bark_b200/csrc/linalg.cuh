@@ -1,0 +1,270 @@
+// CTA-cooperative FP64 dense linear algebra for SPD matrices resident in global memory (L2/HBM).
+//
+// One building block -- a blocked symmetric sweep (block Gauss-Jordan on the lower triangle, pivot blocks
+// of NB = 64) -- serves both uses on the BARK path:
+//   * FULL = false : forward elimination only (a square-root-free block Cholesky, i.e. block LDL^T):
+//                    yields log|W| and y^T W^-1 y in n^3/3 flops.  W is pure workspace.
+//   * FULL = true  : sweep every pivot block over the whole lower triangle: W <- W^-1 (symmetric, both
+//                    triangles written) and log|W| in n^3 flops.
+// The trailing updates are NT GEMMs on 128x128 output tiles with an 8x4 register micro-tile per thread
+// (512 threads), operands staged through shared memory; the 64x64 pivot blocks are inverted in shared
+// memory by a scalar sweep that also produces the pivots for the log-determinant.
+//
+// Replaces np.linalg.inv / np.linalg.slogdet of src/bark/fitting/bark_sampler.py:160-161,269-270 and
+// src/bark/tree_kernels/tree_gps.py:102.
+#pragma once
+#include "common.cuh"
+
+namespace bark {
+namespace la {
+
+constexpr int THREADS = 512;
+constexpr int TILE = 128;  // CTA output tile edge
+constexpr int KB = 32;     // k-step staged in shared memory
+constexpr int NB = 64;     // pivot block size
+
+struct __align__(16) Smem {
+    double As[TILE][KB + 1];
+    double Bs[TILE][KB + 1];
+    double D[NB][NB + 1];
+    double colv[NB];
+    double rowv[NB];
+    double piv[NB];
+    double tv[NB];
+    double red[32];
+};
+
+enum { ACC_SUB = 0, ACC_SET = 1 };
+
+// C[0:mr, 0:nc] (-)= A[0:mr, 0:K] * B[0:nc, 0:K]^T.  Row-major, leading dimensions lda/ldb/ldc.
+// lower_only: write only entries with column <= row (diagonal tiles of a symmetric update).
+// C may alias A (same rows): all global reads of A complete before the first write of C.
+template <int MODE>
+__device__ __forceinline__ void gemm_nt_tile(double* C, int64_t ldc, const double* A, int64_t lda, const double* B,
+                                             int64_t ldb, int mr, int nc, int K, bool lower_only, Smem& s) {
+    const int tid = threadIdx.x, ty = tid >> 5, tx = tid & 31;
+    double acc[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+
+    for (int k0 = 0; k0 < K; k0 += KB) {
+        __syncthreads();
+        for (int e = tid; e < TILE * KB; e += THREADS) {
+            const int r = e >> 5, k = e & 31;
+            double va = 0.0, vb = 0.0;
+            if (k0 + k < K) {
+                if (r < mr) va = A[(int64_t)r * lda + k0 + k];
+                if (r < nc) vb = B[(int64_t)r * ldb + k0 + k];
+            }
+            s.As[r][k] = va;
+            s.Bs[r][k] = vb;
+        }
+        __syncthreads();
+#pragma unroll 4
+        for (int kk = 0; kk < KB; ++kk) {
+            double a[8], b[4];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) a[i] = s.As[ty * 8 + i][kk];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) b[j] = s.Bs[tx + 32 * j][kk];
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int r = ty * 8 + i;
+        if (r < mr) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int c = tx + 32 * j;
+                if (c < nc && (!lower_only || c <= r)) {
+                    double* p = C + (int64_t)r * ldc + c;
+                    if (MODE == ACC_SUB)
+                        *p -= acc[i][j];
+                    else
+                        *p = acc[i][j];
+                }
+            }
+        }
+    }
+}
+
+// Load the bs x bs diagonal block at G (lower triangle valid) into s.D, symmetrised, identity-padded to NB.
+__device__ __forceinline__ void load_pivot_block(const double* G, int64_t ld, int bs, Smem& s) {
+    for (int e = threadIdx.x; e < NB * NB; e += THREADS) {
+        const int r = e / NB, c = e % NB;
+        double v;
+        if (r < bs && c < bs)
+            v = (c <= r) ? G[(int64_t)r * ld + c] : G[(int64_t)c * ld + r];
+        else
+            v = (r == c) ? 1.0 : 0.0;
+        s.D[r][c] = v;
+    }
+    __syncthreads();
+}
+
+// Scalar symmetric sweep of s.D over all NB pivots: s.D <- -D^-1, s.piv[j] <- j-th pivot (successive
+// Schur complements; their product is det D).  Returns false (uniformly) if a pivot is not positive.
+__device__ __forceinline__ bool sweep_pivot_block(Smem& s) {
+    const int tid = threadIdx.x;
+    bool ok = true;
+    for (int j = 0; j < NB; ++j) {
+        __syncthreads();
+        const double p = s.D[j][j];
+        if (tid < NB) {
+            s.colv[tid] = s.D[tid][j];
+            s.rowv[tid] = s.D[j][tid];
+        }
+        if (tid == 0) s.piv[j] = p;
+        if (!(p > 0.0)) ok = false;
+        const double ip = 1.0 / p;
+        __syncthreads();
+        for (int e = tid; e < NB * NB; e += THREADS) {
+            const int r = e / NB, c = e % NB;
+            double v;
+            if (r == j && c == j)
+                v = -ip;
+            else if (r == j)
+                v = s.rowv[c] * ip;
+            else if (c == j)
+                v = s.colv[r] * ip;
+            else
+                v = s.D[r][c] - s.colv[r] * ip * s.rowv[c];
+            s.D[r][c] = v;
+        }
+    }
+    __syncthreads();
+    return ok;
+}
+
+// Blocked symmetric sweep of the n x n SPD matrix W (lower triangle valid on entry, leading dim ld).
+//   CK, GK : scratch panels, n x NB doubles each (row-major, ld = NB).
+//   yv     : optional (FULL == false) mutable copy of a right-hand side; on exit *quad = y^T W^-1 y.
+// Returns log|W| to every thread.  *status |= BARK_ST_NOT_SPD on a non-positive pivot.
+template <bool FULL>
+__device__ double block_sweep(double* W, int64_t ld, int n, double* CK, double* GK, double* yv, double* quad,
+                              Smem& s, uint32_t* status) {
+    const int tid = threadIdx.x;
+    const int nblk = (n + NB - 1) / NB;
+    double logdet = 0.0, q = 0.0;
+    for (int kb = 0; kb < nblk; ++kb) {
+        const int k0 = kb * NB;
+        const int bs = min(NB, n - k0);
+        load_pivot_block(W + (int64_t)k0 * ld + k0, ld, bs, s);
+        const bool ok = sweep_pivot_block(s);  // s.D = -Dinv
+        if (!ok && tid == 0 && status) atomicOr(status, BARK_ST_NOT_SPD);
+        // log det of the pivot block
+        {
+            double lg = (tid < NB) ? log(s.piv[tid]) : 0.0;
+            logdet += block_sum(lg, s.red);
+        }
+        // right-hand side elimination (forward mode): t = Dinv y_k ; quad += y_k^T t
+        if (!FULL && yv) {
+            if (tid < NB) {
+                double t = 0.0;
+                if (tid < bs)
+                    for (int c = 0; c < bs; ++c) t -= s.D[tid][c] * yv[k0 + c];
+                s.tv[tid] = t;
+            }
+            __syncthreads();
+            double part = (tid < bs) ? s.tv[tid] * yv[k0 + tid] : 0.0;
+            q += block_sum(part, s.red);
+        }
+        const int rlo = FULL ? 0 : k0 + bs;  // first row taking part in the update
+        if (rlo >= n && !FULL) break;
+        // gather the pivot block column: CK[i][c] = W[i][k0+c] (i below) or W[k0+c][i] (i above); 0 inside block
+        for (int64_t e = tid; e < (int64_t)(n - rlo) * NB; e += THREADS) {
+            const int i = rlo + (int)(e / NB), c = (int)(e % NB);
+            double v = 0.0;
+            if (c < bs) {
+                if (i >= k0 + bs)
+                    v = W[(int64_t)i * ld + k0 + c];
+                else if (i < k0)
+                    v = W[(int64_t)(k0 + c) * ld + i];
+            }
+            CK[(int64_t)i * NB + c] = v;
+        }
+        // Dinv into global scratch? -- no: GK = CK * Dinv computed straight from shared memory (Dinv = -s.D).
+        __syncthreads();
+        for (int64_t e = tid; e < (int64_t)(n - rlo) * NB; e += THREADS) {
+            const int i = rlo + (int)(e / NB), c = (int)(e % NB);
+            const double* ck = CK + (int64_t)i * NB;
+            double g = 0.0;
+#pragma unroll 8
+            for (int k = 0; k < NB; ++k) g -= ck[k] * s.D[k][c];
+            GK[(int64_t)i * NB + c] = g;
+        }
+        // forward mode: y_r -= G_r . y_k = C_r . t
+        if (!FULL && yv) {
+            for (int i = rlo + tid; i < n; i += THREADS) {
+                const double* ck = CK + (int64_t)i * NB;
+                double a = 0.0;
+                for (int c = 0; c < bs; ++c) a += ck[c] * s.tv[c];
+                yv[i] -= a;
+            }
+        }
+        __syncthreads();
+        // trailing update on the lower triangle: W_ij -= G_i C_j^T
+        for (int ti = rlo; ti < n; ti += TILE) {
+            const int mr = min(TILE, n - ti);
+            for (int tj = rlo; tj <= ti; tj += TILE) {
+                const int nc = min(TILE, n - tj);
+                gemm_nt_tile<ACC_SUB>(W + (int64_t)ti * ld + tj, ld, GK + (int64_t)ti * NB, NB, CK + (int64_t)tj * NB,
+                                      NB, mr, nc, bs, ti == tj, s);
+            }
+        }
+        if (FULL) {
+            __syncthreads();
+            // write the swept pivot column/row back: W_ik = G_i (i below), W_kj = G_j^T (j above), W_kk = -Dinv
+            for (int64_t e = tid; e < (int64_t)n * NB; e += THREADS) {
+                const int i = (int)(e / NB), c = (int)(e % NB);
+                if (c >= bs) continue;
+                if (i >= k0 + bs)
+                    W[(int64_t)i * ld + k0 + c] = GK[(int64_t)i * NB + c];
+                else if (i < k0)
+                    W[(int64_t)(k0 + c) * ld + i] = GK[(int64_t)i * NB + c];
+                else if (c <= i - k0)
+                    W[(int64_t)i * ld + k0 + c] = s.D[i - k0][c];
+            }
+        }
+        __syncthreads();
+    }
+    if (FULL) {
+        // W currently holds -W^-1 on the lower triangle: negate and mirror (32x32 tiles through shared memory).
+        __syncthreads();
+        double(*T)[33] = reinterpret_cast<double(*)[33]>(&s.As[0][0]);  // 32 x 33 tile
+        const int tx = tid & 31, ty = tid >> 5;                            // 32 x 16
+        const int nt = (n + 31) / 32;
+        for (int bi = 0; bi < nt; ++bi) {
+            for (int bj = 0; bj <= bi; ++bj) {
+                __syncthreads();
+                for (int r = ty; r < 32; r += 16) {
+                    const int gi = bi * 32 + r, gj = bj * 32 + tx;
+                    double v = 0.0;
+                    if (gi < n && gj < n && gj <= gi) {
+                        v = -W[(int64_t)gi * ld + gj];
+                        W[(int64_t)gi * ld + gj] = v;
+                    }
+                    T[r][tx] = v;
+                }
+                __syncthreads();
+                for (int r = ty; r < 32; r += 16) {
+                    // element (gj2, gi2) of the upper triangle = T[tx][r] transposed
+                    const int gi = bj * 32 + r, gj = bi * 32 + tx;  // row in block bj, column in block bi
+                    if (gi < n && gj < n && gj > gi) W[(int64_t)gi * ld + gj] = T[tx][r];
+                }
+            }
+        }
+        __syncthreads();
+    }
+    if (quad) *quad = q;
+    return logdet;
+}
+
+}  // namespace la
+}  // namespace bark

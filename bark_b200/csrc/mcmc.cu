@@ -1,0 +1,746 @@
+// a8-a13: device-resident BARK MCMC in leaf space (see mcmc_state.cuh for the algebra).
+//
+//   bark_mcmc_init    chain state from (forest, noise, scale)          bark_sampler.py:147-162
+//   bark_mcmc_sweeps  m tree MH steps + 1 noise/scale MH step / sweep  bark_sampler.py:216-284
+//
+// Every tree move is the rank-one change  Z' = Z + u d^T  of the leaf-indicator matrix
+// (u in {-1,0,1}^n marks the training points that change leaf, d = e_a - e_b names the two columns):
+//     grow   leaf (col p) -> L keeps p, R gets a free column f :  u = 1[R],          d = e_f  - e_p
+//     prune  children (pL, pR) merge into pL                    :  u = 1[R],          d = e_pL - e_pR
+//     change children (pL, pR) re-split                         :  u = 1[L->R]-1[R->L], d = e_pR - e_pL
+// hence  B' = B + [d v] [[n_u,1],[1,0]] [d v]^T  with  v = Z^T u  (AND+POPC on the leaf bitsets),
+// n_u = u^T u, b' = b + (u^T y) d, and the proposal's log-MLL follows from ONE matvec  Binv v  (none for
+// prune, where Binv v = e_b - c Binv[:,b]) plus O(P) dot products (2x2 capacitance matrix).  On accept the
+// state takes a symmetric rank-2 update.  One CTA owns one chain for the whole sweep.
+#include <algorithm>
+
+#include "common.cuh"
+#include "forest_device.cuh"
+#include "linalg.cuh"
+#include "mcmc_state.cuh"
+#include "proposal_device.cuh"
+
+namespace bark {
+
+// =====================================================================================================
+// setup: shared inputs into the workspace (X transposed to feature-major, y, bounds, feat_types)
+// =====================================================================================================
+__global__ void ws_setup_kernel(WsLayout lay, void* ws, const double* __restrict__ X, const double* __restrict__ y,
+                                const double* __restrict__ bounds, const int32_t* __restrict__ ft) {
+    unsigned char* base = (unsigned char*)ws;
+    double* Xt = (double*)(base + lay.off_xt);
+    double* yy = (double*)(base + lay.off_y);
+    double* bb = (double*)(base + lay.off_bounds);
+    int32_t* ff = (int32_t*)(base + lay.off_ft);
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t e = tid; e < lay.d * lay.npad; e += nth) {
+        const int64_t f = e / lay.npad, i = e % lay.npad;
+        Xt[e] = (i < lay.n) ? X[i * lay.d + f] : 0.0;
+    }
+    for (int64_t e = tid; e < lay.npad; e += nth) yy[e] = (e < lay.n) ? y[e] : 0.0;
+    for (int64_t e = tid; e < lay.d * 2; e += nth) bb[e] = bounds ? bounds[e] : 0.0;
+    for (int64_t e = tid; e < lay.d; e += nth) ff[e] = ft[e];
+}
+
+// =====================================================================================================
+// helpers shared by init / hyper kernels (512 threads)
+// =====================================================================================================
+// w = Binv b over [0, ph); returns q = b^T w (to all threads).  Deterministic.
+__device__ double matvec_w_q(const double* __restrict__ Binv, int P, int ph, const double* __restrict__ b, double* w,
+                             double* red) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int r = wid; r < ph; r += nw) {
+        const double* row = Binv + (size_t)r * P;
+        double acc = 0.0;
+        for (int k = lane; k < ph; k += 32) acc = fma(row[k], b[k], acc);
+        acc = warp_sum(acc);
+        if (lane == 0) w[r] = acc;
+    }
+    __syncthreads();
+    double part = 0.0;
+    for (int k = threadIdx.x; k < ph; k += blockDim.x) part = fma(b[k], w[k], part);
+    return block_sum(part, red);
+}
+
+__device__ __forceinline__ double mll_from(double yy, double q, double sig, double n, double ldt) {
+    return 0.5 * (-(yy - q) / sig - n * log(sig) - ldt);
+}
+
+// Fill W[0:ph,0:ph] lower triangle with A + c I.
+__device__ void fill_B_lower(double* W, const int32_t* __restrict__ A, int P, int ph, double c) {
+    for (int64_t e = threadIdx.x; e < (int64_t)ph * ph; e += blockDim.x) {
+        const int r = (int)(e / ph), k = (int)(e % ph);
+        if (k <= r) W[(size_t)r * P + k] = (double)A[(size_t)r * P + k] + (r == k ? c : 0.0);
+    }
+}
+
+// =====================================================================================================
+// chain init: columns, bitsets, A, b, Binv, scalars.  One CTA (512 threads) per chain.
+// =====================================================================================================
+__global__ void __launch_bounds__(la::THREADS, 1)
+chain_init_kernel(WsLayout lay, void* ws, bark_nodes_soa forest, const double* __restrict__ noise,
+                  const double* __restrict__ scale) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    la::Smem& s = *reinterpret_cast<la::Smem*>(smem_raw);
+    WalkNode* wn = reinterpret_cast<WalkNode*>(smem_raw + sizeof(la::Smem));  // [L]
+    int* ftc = reinterpret_cast<int*>(wn + lay.L);                             // [d]
+    int* tcount = ftc + lay.d;                                                 // [m + 1]
+
+    const int64_t chain = blockIdx.x;
+    ChainView cv = chain_view(lay, ws, chain);
+    SharedView sv = shared_view(lay, ws);
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = la::THREADS >> 5;
+    const int P = (int)lay.P, L = (int)lay.L, m = (int)lay.m, n = (int)lay.n, wd = (int)lay.wd, npad = (int)lay.npad;
+    const int64_t nb = chain * (int64_t)m * L;
+
+    // ---- 1. one column per active leaf, numbered in (tree, slot) order
+    for (int t = tid; t < m; t += la::THREADS) {
+        int c = 0;
+        for (int sl = 0; sl < L; ++sl) c += (forest.active[nb + (int64_t)t * L + sl] && forest.is_leaf[nb + (int64_t)t * L + sl]);
+        tcount[t + 1] = c;
+    }
+    for (int e = tid; e < lay.d; e += la::THREADS) ftc[e] = sv.ft[e];
+    __syncthreads();
+    if (tid == 0) {
+        tcount[0] = 0;
+        for (int t = 0; t < m; ++t) tcount[t + 1] += tcount[t];
+    }
+    __syncthreads();
+    const int ptot = tcount[m];
+    if (ptot > P) {
+        if (tid == 0) {
+            cv.sc->status = BARK_ST_COL_OVERFLOW;
+            cv.sc->p_hi = 0;
+        }
+        return;
+    }
+    for (int t = tid; t < m; t += la::THREADS) {
+        int c = tcount[t];
+        for (int sl = 0; sl < L; ++sl) {
+            const int64_t g = nb + (int64_t)t * L + sl;
+            cv.colmap[t * L + sl] = (forest.active[g] && forest.is_leaf[g]) ? (uint16_t)(c++) : NO_COL;
+        }
+    }
+    for (int w = tid; w < P / 32; w += la::THREADS) {
+        const int lo = w * 32;
+        cv.colused[w] = (ptot >= lo + 32) ? 0xFFFFFFFFu : (ptot <= lo ? 0u : ((1u << (ptot - lo)) - 1u));
+    }
+    for (int64_t e = tid; e < (int64_t)P * wd; e += la::THREADS) cv.bits[e] = 0u;
+    __syncthreads();
+
+    // ---- 2. leaf bitsets: walk every training point down every tree (tree staged in shared memory)
+    for (int t = 0; t < m; ++t) {
+        __syncthreads();
+        for (int e = tid; e < L; e += la::THREADS) {
+            const int64_t g = nb + (int64_t)t * L + e;
+            wn[e] = make_walk_node(forest.is_leaf[g], forest.feature[g], forest.threshold[g], forest.left[g],
+                                   forest.right[g]);
+        }
+        __syncthreads();
+        for (int w = wid; w < wd; w += nw) {
+            const int i = w * 32 + lane;
+            unsigned col = 0xFFFFFFFFu;
+            if (i < n) col = cv.colmap[t * L + walk_tree(wn, sv.Xt + i, npad, ftc, L)];
+            const unsigned grp = __match_any_sync(0xffffffffu, col);
+            if (i < n && col != NO_COL && lane == __ffs(grp) - 1) cv.bits[(size_t)col * wd + w] = grp;
+        }
+    }
+    __syncthreads();
+
+    // ---- 3. A = Z^T Z (AND + POPC), b = Z^T y
+    for (int64_t e = tid; e < (int64_t)P * P; e += la::THREADS) {
+        const int r = (int)(e / P), k = (int)(e % P);
+        int cnt = 0;
+        if (r < ptot && k < ptot) {
+            const uint32_t* br = cv.bits + (size_t)r * wd;
+            const uint32_t* bk = cv.bits + (size_t)k * wd;
+            for (int w = 0; w < wd; ++w) cnt += __popc(br[w] & bk[w]);
+        }
+        cv.A[e] = cnt;
+    }
+    for (int p = wid; p < P; p += nw) {
+        double acc = 0.0;
+        if (p < ptot)
+            for (int w = lane; w < wd; w += 32) {
+                uint32_t bw = cv.bits[(size_t)p * wd + w];
+                while (bw) {
+                    const int bit = __ffs(bw) - 1;
+                    bw &= bw - 1;
+                    acc += sv.y[w * 32 + bit];
+                }
+            }
+        acc = warp_sum(acc);
+        if (lane == 0) {
+            cv.b[p] = acc;
+            cv.w[p] = 0.0;
+        }
+    }
+    double part = 0.0;
+    for (int i = tid; i < n; i += la::THREADS) part = fma(sv.y[i], sv.y[i], part);
+    const double yy = block_sum(part, s.red);
+
+    // ---- 4. Binv = (c I + A)^-1, ldt, q, mll
+    const double sig = noise[chain] + 1e-6;
+    const double c = sig * (double)m / scale[chain];
+    for (int64_t e = tid; e < (int64_t)P * P; e += la::THREADS) {
+        const int r = (int)(e / P), k = (int)(e % P);
+        cv.Binv[e] = (r == k) ? 1.0 / c : 0.0;
+    }
+    __syncthreads();
+    fill_B_lower(cv.Binv, cv.A, P, ptot, c);
+    __syncthreads();
+    unsigned* stp = &cv.sc->status;
+    if (tid == 0) *stp = 0;
+    __syncthreads();
+    const double logdet = la::block_sweep<true>(cv.Binv, P, ptot, cv.CK, cv.GK, nullptr, nullptr, s, stp);
+    const double q = matvec_w_q(cv.Binv, P, ptot, cv.b, cv.w, s.red);
+    const double ldt = logdet - (double)ptot * log(c);
+    if (tid == 0) {
+        ChainScalars* sc = cv.sc;
+        sc->noise = noise[chain];
+        sc->scale = scale[chain];
+        sc->sig = sig;
+        sc->c = c;
+        sc->q = q;
+        sc->ldt = ldt;
+        sc->yy = yy;
+        sc->mll = mll_from(yy, q, sig, (double)n, ldt);
+        for (int k = 0; k < 8; ++k) sc->counters[k] = 0ull;
+        sc->p_hi = ptot;
+    }
+}
+
+// =====================================================================================================
+// tree sweep: one CTA (1024 threads) per chain runs the m tree MH steps of one sweep
+// =====================================================================================================
+constexpr int SW_THREADS = 1024;
+
+struct SweepCtl {  // small shared control block
+    Prop prop;
+    double q, ldt, mll;
+    int p_hi;
+    int accept;
+};
+
+__host__ __device__ inline size_t sweep_smem_bytes(int L, int d, int P, int wd) {
+    size_t o = 0;
+    o += align256(sizeof(SweepCtl));
+    o += align256((size_t)L * 2);        // is_leaf, active
+    o += align256((size_t)L * 4 * 6);    // feat,left,right,parent,depth,thr
+    o += align256((size_t)d * 2 * 8);    // box
+    o += align256((size_t)d * 4);        // ft
+    o += align256((size_t)P * 8) * 3;    // vd, Wd, Wv
+    o += align256((size_t)wd * 4) * 2;   // upos, uneg
+    o += align256(64 * 8);               // red
+    return o;
+}
+
+__global__ void __launch_bounds__(SW_THREADS, 1)
+sweep_trees_kernel(WsLayout lay, void* ws, bark_nodes_soa forest, bark_params prm, int64_t sweep_in_call,
+                   int64_t n_sweeps_call, uint64_t seed, int64_t chain_offset, int64_t sweep_offset,
+                   const double* __restrict__ tape, double* __restrict__ trace) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int P = (int)lay.P, L = (int)lay.L, m = (int)lay.m, n = (int)lay.n, wd = (int)lay.wd, npad = (int)lay.npad;
+    const int d = (int)lay.d;
+    unsigned char* sp = smem_raw;
+    SweepCtl* ctl = (SweepCtl*)sp;           sp += align256(sizeof(SweepCtl));
+    TreeSmem T;
+    T.is_leaf = sp; T.active = sp + L;       sp += align256((size_t)L * 2);
+    T.feat = (uint32_t*)sp; T.left = T.feat + L; T.right = T.left + L; T.parent = T.right + L; T.depth = T.parent + L;
+    T.thr = (float*)(T.depth + L);           sp += align256((size_t)L * 4 * 6);
+    double* box = (double*)sp;               sp += align256((size_t)d * 2 * 8);
+    int32_t* ftc = (int32_t*)sp;             sp += align256((size_t)d * 4);
+    double* vd = (double*)sp;                sp += align256((size_t)P * 8);
+    double* Wd = (double*)sp;                sp += align256((size_t)P * 8);
+    double* Wv = (double*)sp;                sp += align256((size_t)P * 8);
+    uint32_t* upos = (uint32_t*)sp;          sp += align256((size_t)wd * 4);
+    uint32_t* uneg = (uint32_t*)sp;          sp += align256((size_t)wd * 4);
+    double* red = (double*)sp;
+
+    const int64_t chain = blockIdx.x;
+    ChainView cv = chain_view(lay, ws, chain);
+    SharedView sv = shared_view(lay, ws);
+    ChainScalars* sc = cv.sc;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = SW_THREADS >> 5;
+
+    if (sc->status & (BARK_ST_COL_OVERFLOW | BARK_ST_TREE_OVERFLOW | BARK_ST_HYPER_MODE)) return;  // chain is dead
+
+    const double sig = sc->sig, c = sc->c, yy = sc->yy;
+    const double nlogsig = (double)n * log(sig);
+    if (tid == 0) {
+        ctl->q = sc->q; ctl->ldt = sc->ldt; ctl->mll = sc->mll; ctl->p_hi = sc->p_hi;
+    }
+    for (int e = tid; e < d; e += SW_THREADS) ftc[e] = sv.ft[e];
+    unsigned long long n_valid = 0, n_acc = 0, n_acc_move[3] = {0, 0, 0};  // thread 0 only
+
+    const uint32_t g_chain = (uint32_t)(chain_offset + chain), g_sweep = (uint32_t)(sweep_offset + sweep_in_call);
+    const size_t tape_base = tape ? ((size_t)(chain * n_sweeps_call + sweep_in_call)) * (size_t)(m * TAPE_PER_TREE + TAPE_PER_HYPER) : 0;
+    double* trace_base = trace ? trace + ((size_t)(chain * n_sweeps_call + sweep_in_call)) * (size_t)(m + 1) * 3 : nullptr;
+
+    for (int t = 0; t < m; ++t) {
+        __syncthreads();
+        // ---- stage the tree and the root box
+        const int64_t g0 = (chain * (int64_t)m + t) * L;
+        for (int e = tid; e < L; e += SW_THREADS) {
+            T.is_leaf[e] = forest.is_leaf[g0 + e];
+            T.active[e] = forest.active[g0 + e];
+            T.feat[e] = forest.feature[g0 + e];
+            T.left[e] = forest.left[g0 + e];
+            T.right[e] = forest.right[g0 + e];
+            T.parent[e] = forest.parent[g0 + e];
+            T.depth[e] = forest.depth[g0 + e];
+            T.thr[e] = forest.threshold[g0 + e];
+        }
+        for (int e = tid; e < 2 * d; e += SW_THREADS) box[e] = sv.bounds[e];
+        __syncthreads();
+
+        // ---- proposal (warp 0)
+        double u[6];
+        if (wid == 0) {
+            if (tape) {
+                for (int k = 0; k < TAPE_PER_TREE; ++k) u[k] = tape[tape_base + (size_t)t * TAPE_PER_TREE + k];
+            } else {
+                rng_uniforms(seed, g_chain, g_sweep, (uint32_t)t, TAPE_PER_TREE, u);
+            }
+            Prop p = propose_tree_warp(T, L, box, ftc, d, cv.colmap + (size_t)t * L, cv.colused, P, prm, u, &sc->status);
+            if (lane == 0) ctl->prop = p;
+        }
+        __syncthreads();
+        const Prop p = ctl->prop;
+        const double cur_q = ctl->q, cur_ldt = ctl->ldt, cur_mll = ctl->mll;
+        const int p_hi = ctl->p_hi;
+
+        double new_q = cur_q, new_ldt = cur_ldt, new_mll = cur_mll;
+        double eta = 0.0, n_u = 0.0, M00 = 0.0, M01 = 0.0, M11 = 0.0, det = -1.0, Ur0 = 0.0, Ur1 = 0.0;
+        int pe64 = 0;
+        bool accept = false;
+
+        if (p.valid) {
+            const int a = p.a, b = p.b;
+            const int pe = max(p_hi, max(a, b) + 1);
+            pe64 = min(P, (pe + 63) & ~63);
+            // ---- phase 1: the moved-point masks u+ / u-, eta = u^T y, n_u = u^T u
+            double eta_part = 0.0;
+            int cnt_part = 0;
+            const uint32_t* bits_a = cv.bits + (size_t)a * wd;
+            const uint32_t* bits_b = cv.bits + (size_t)b * wd;
+            const double* xf = sv.Xt + (size_t)p.feat * npad;
+            const int ftype = ftc[p.feat];
+            for (int i = tid; i < npad; i += SW_THREADS) {
+                const int w = i >> 5;
+                bool pos = false, neg = false;
+                if (i < n) {
+                    const bool in_b = (bits_b[w] >> lane) & 1u;
+                    if (p.move == MOVE_GROW) {
+                        if (in_b) pos = !goes_left(xf[i], p.thr, ftype);
+                    } else if (p.move == MOVE_PRUNE) {
+                        pos = in_b;
+                    } else {  // change: b = left child's column, a = right child's column
+                        const bool in_a = (bits_a[w] >> lane) & 1u;
+                        if (in_a || in_b) {
+                            const bool gl = goes_left(xf[i], p.thr, ftype);
+                            pos = in_b && !gl;
+                            neg = in_a && gl;
+                        }
+                    }
+                    if (pos) { eta_part += sv.y[i]; ++cnt_part; }
+                    if (neg) { eta_part -= sv.y[i]; ++cnt_part; }
+                }
+                const unsigned bp = __ballot_sync(0xffffffffu, pos), bn = __ballot_sync(0xffffffffu, neg);
+                if (lane == 0) { upos[w] = bp; uneg[w] = bn; }
+            }
+            eta = block_sum(eta_part, red);
+            n_u = block_sum((double)cnt_part, red);  // exact (integers < 2^53)
+            // (block_sum ends with every thread past its barriers; upos/uneg are visible)
+
+            // ---- phase 2: v = Z^T u by AND + POPC over the leaf bitsets
+            for (int q = wid; q < pe64; q += nw) {
+                int cnt = 0;
+                if (q < pe) {
+                    const uint32_t* bq = cv.bits + (size_t)q * wd;
+                    for (int w = lane; w < wd; w += 32) {
+                        const uint32_t x = bq[w];
+                        cnt += __popc(x & upos[w]) - __popc(x & uneg[w]);
+                    }
+                }
+                cnt = warp_sum_int(cnt);
+                if (lane == 0) vd[q] = (double)cnt;
+            }
+            // ---- phase 3: Wd = Binv d (two rows), Wv = Binv v (matvec; closed form for prune)
+            const double* row_a = cv.Binv + (size_t)a * P;
+            const double* row_b = cv.Binv + (size_t)b * P;
+            for (int k = tid; k < pe64; k += SW_THREADS) Wd[k] = row_a[k] - row_b[k];
+            __syncthreads();
+            if (p.move == MOVE_PRUNE) {
+                for (int k = tid; k < pe64; k += SW_THREADS) Wv[k] = ((k == b) ? 1.0 : 0.0) - c * row_b[k];
+            } else {
+                for (int q = wid; q < pe64; q += nw) {
+                    const double* row = cv.Binv + (size_t)q * P;
+                    double acc0 = 0.0, acc1 = 0.0;
+#pragma unroll 4
+                    for (int k = lane * 2; k < pe64; k += 64) {
+                        const double2 x = *reinterpret_cast<const double2*>(row + k);
+                        const double2 vv = *reinterpret_cast<const double2*>(vd + k);
+                        acc0 = fma(x.x, vv.x, acc0);
+                        acc1 = fma(x.y, vv.y, acc1);
+                    }
+                    const double acc = warp_sum(acc0 + acc1);
+                    if (lane == 0) Wv[q] = acc;
+                }
+            }
+            __syncthreads();
+            // ---- phase 4: 2x2 capacitance matrix and the proposed log-MLL
+            double pvv = 0.0, pvw = 0.0;
+            for (int k = tid; k < pe64; k += SW_THREADS) {
+                pvv = fma(vd[k], Wv[k], pvv);
+                pvw = fma(vd[k], cv.w[k], pvw);
+            }
+            const double vWv = block_sum(pvv, red);
+            const double vw = block_sum(pvw, red);
+            const double dWd = Wd[a] - Wd[b];
+            const double dWv = Wv[a] - Wv[b];
+            const double dw = cv.w[a] - cv.w[b];
+            M00 = dWd;
+            M01 = 1.0 + dWv;
+            M11 = -n_u + vWv;
+            det = M00 * M11 - M01 * M01;                 // < 0 for an SPD B'
+            new_ldt = cur_ldt + log(-det);
+            const double bq = cur_q + 2.0 * eta * dw + eta * eta * dWd;  // b'^T Binv b'
+            Ur0 = dw + eta * dWd;                                         // d^T r,  r = Binv b'
+            Ur1 = vw + eta * dWv;                                         // v^T r
+            new_q = bq - (M11 * Ur0 * Ur0 - 2.0 * M01 * Ur0 * Ur1 + M00 * Ur1 * Ur1) / det;
+            new_mll = 0.5 * (-(yy - new_q) / sig - nlogsig - new_ldt);
+        }
+
+        // ---- MH accept (bark_sampler.py:257-264); every thread evaluates the same scalars
+        {
+            double u_acc;
+            if (tape) u_acc = tape[tape_base + (size_t)t * TAPE_PER_TREE + 4];
+            else {
+                double uu[6];
+                rng_uniforms(seed, g_chain, g_sweep, (uint32_t)t, TAPE_PER_TREE, uu);
+                u_acc = uu[4];
+            }
+            if (p.valid) {
+                const double log_alpha = p.lqp + (new_mll - cur_mll);
+                accept = log(u_acc) <= fmin(log_alpha, 0.0);
+            }
+            if (tid == 0) {
+                if (trace_base) {
+                    trace_base[t * 3 + 0] = p.valid ? p.lqp : -INFINITY;
+                    trace_base[t * 3 + 1] = new_mll;
+                    trace_base[t * 3 + 2] = accept ? 1.0 : 0.0;
+                }
+                n_valid += p.valid ? 1 : 0;
+            }
+        }
+
+        if (accept) {
+            __syncthreads();  // every thread has finished reading w / Binv for the evaluation
+            const int a = p.a, b = p.b;
+            // M^-1 = [[al, be],[be, ga]]
+            const double al = M11 / det, be = -M01 / det, ga = M00 / det;
+            const double cw_d = al * Ur0 + be * Ur1, cw_v = be * Ur0 + ga * Ur1;
+            // w' = (w + eta Wd) - Wd cw_d - Wv cw_v
+            for (int k = tid; k < pe64; k += SW_THREADS) cv.w[k] = cv.w[k] + eta * Wd[k] - Wd[k] * cw_d - Wv[k] * cw_v;
+            // Binv' = Binv - [Wd Wv] M^-1 [Wd Wv]^T   (symmetric rank-2, read-modify-write)
+            for (int q = wid; q < pe64; q += nw) {
+                double* row = cv.Binv + (size_t)q * P;
+                const double cq_d = al * Wd[q] + be * Wv[q], cq_v = be * Wd[q] + ga * Wv[q];
+#pragma unroll 4
+                for (int k = lane * 2; k < pe64; k += 64) {
+                    double2 x = *reinterpret_cast<double2*>(row + k);
+                    const double2 dd = *reinterpret_cast<const double2*>(Wd + k);
+                    const double2 vv = *reinterpret_cast<const double2*>(Wv + k);
+                    x.x -= cq_d * dd.x + cq_v * vv.x;
+                    x.y -= cq_d * dd.y + cq_v * vv.y;
+                    *reinterpret_cast<double2*>(row + k) = x;
+                }
+            }
+            // A' = A + v d^T + d v^T + n_u d d^T  (exact integers): columns, then rows, then the corner
+            for (int k = tid; k < pe64; k += SW_THREADS) {
+                const int vk = (int)vd[k];
+                cv.A[(size_t)k * P + a] += vk;
+                cv.A[(size_t)k * P + b] -= vk;
+            }
+            __syncthreads();
+            for (int k = tid; k < pe64; k += SW_THREADS) {
+                const int vk = (int)vd[k];
+                cv.A[(size_t)a * P + k] += vk;
+                cv.A[(size_t)b * P + k] -= vk;
+            }
+            // leaf bitsets
+            for (int w = tid; w < wd; w += SW_THREADS) {
+                const uint32_t ba = cv.bits[(size_t)a * wd + w], bb = cv.bits[(size_t)b * wd + w];
+                cv.bits[(size_t)a * wd + w] = (ba | upos[w]) & ~uneg[w];
+                cv.bits[(size_t)b * wd + w] = (bb & ~upos[w]) | uneg[w];
+            }
+            __syncthreads();
+            if (tid == 0) {
+                // corner term n_u d d^T
+                const int nuu = (int)n_u;
+                cv.A[(size_t)a * P + a] += nuu;
+                cv.A[(size_t)b * P + b] += nuu;
+                cv.A[(size_t)a * P + b] -= nuu;
+                cv.A[(size_t)b * P + a] -= nuu;
+                cv.b[a] += eta;
+                cv.b[b] -= eta;
+                // forest edit (tree_proposals.py:146-183) + column bookkeeping
+                uint16_t* cm = cv.colmap + (size_t)t * L;
+                if (p.move == MOVE_GROW) {
+                    const uint32_t dep = T.depth[p.node];
+                    for (int s2 = 0; s2 < 2; ++s2) {
+                        const int64_t g = g0 + (s2 ? p.sr : p.sl);
+                        forest.is_leaf[g] = 1; forest.feature[g] = 0; forest.threshold[g] = 0.f; forest.left[g] = 0;
+                        forest.right[g] = 0; forest.parent[g] = (uint32_t)p.node; forest.depth[g] = dep + 1;
+                        forest.active[g] = 1;
+                    }
+                    const int64_t g = g0 + p.node;
+                    forest.is_leaf[g] = 0; forest.feature[g] = (uint32_t)p.feat; forest.threshold[g] = p.thr;
+                    forest.left[g] = (uint32_t)p.sl; forest.right[g] = (uint32_t)p.sr; forest.active[g] = 1;
+                    cm[p.sl] = (uint16_t)b;   // left child keeps the old leaf's column
+                    cm[p.sr] = (uint16_t)a;   // right child takes the new column
+                    cm[p.node] = NO_COL;
+                    cv.colused[a >> 5] |= (1u << (a & 31));
+                    if (a + 1 > ctl->p_hi) ctl->p_hi = a + 1;
+                } else if (p.move == MOVE_PRUNE) {
+                    forest.active[g0 + p.sl] = 0;
+                    forest.active[g0 + p.sr] = 0;
+                    forest.is_leaf[g0 + p.node] = 1;
+                    cm[p.node] = (uint16_t)a;  // merged leaf keeps the left child's column
+                    cm[p.sl] = NO_COL;
+                    cm[p.sr] = NO_COL;
+                    cv.colused[b >> 5] &= ~(1u << (b & 31));
+                    cv.b[b] = 0.0;
+                } else {
+                    forest.feature[g0 + p.node] = (uint32_t)p.feat;
+                    forest.threshold[g0 + p.node] = p.thr;
+                }
+                ctl->q = new_q; ctl->ldt = new_ldt; ctl->mll = new_mll;
+                ++n_acc;
+                ++n_acc_move[p.move];
+            }
+            if (p.move == MOVE_PRUNE) {
+                // column b is now an empty leaf: make its row / column of Binv exactly (1/c) e_b
+                __syncthreads();
+                for (int k = tid; k < pe64; k += SW_THREADS) {
+                    const double v = (k == b) ? 1.0 / c : 0.0;
+                    cv.Binv[(size_t)b * P + k] = v;
+                    cv.Binv[(size_t)k * P + b] = v;
+                }
+                if (tid == 0) cv.w[b] = 0.0;
+            }
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        sc->q = ctl->q; sc->ldt = ctl->ldt; sc->mll = ctl->mll; sc->p_hi = ctl->p_hi;
+        sc->counters[0] += (unsigned long long)m;
+        sc->counters[1] += n_valid;
+        sc->counters[2] += n_acc;
+        sc->counters[5] += n_acc_move[0];
+        sc->counters[6] += n_acc_move[1];
+        sc->counters[7] += n_acc_move[2];
+    }
+}
+
+// =====================================================================================================
+// hyper step: noise/scale MH with a full re-evaluation (bark_sampler.py:266-282).  One CTA per chain.
+// =====================================================================================================
+__global__ void __launch_bounds__(la::THREADS, 1)
+hyper_kernel(WsLayout lay, void* ws, bark_params prm, int64_t sweep_in_call, int64_t n_sweeps_call, uint64_t seed,
+             int64_t chain_offset, int64_t sweep_offset, const double* __restrict__ tape, double* __restrict__ trace) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    la::Smem& s = *reinterpret_cast<la::Smem*>(smem_raw);
+    __shared__ HyperProp hp;
+    __shared__ int s_phi;
+    __shared__ double s_uacc;
+    const int64_t chain = blockIdx.x;
+    ChainView cv = chain_view(lay, ws, chain);
+    ChainScalars* sc = cv.sc;
+    const int tid = threadIdx.x;
+    const int P = (int)lay.P, m = (int)lay.m, n = (int)lay.n;
+    if (sc->status & (BARK_ST_COL_OVERFLOW | BARK_ST_TREE_OVERFLOW | BARK_ST_HYPER_MODE)) return;
+
+    const size_t per = (size_t)(m * TAPE_PER_TREE + TAPE_PER_HYPER);
+    if (tid == 0) {
+        double zn, zs, ua;
+        if (tape) {
+            const double* tp = tape + ((size_t)(chain * n_sweeps_call + sweep_in_call)) * per + (size_t)m * TAPE_PER_TREE;
+            zn = tp[0]; zs = tp[1]; ua = tp[2];
+        } else {
+            double u[6];
+            rng_uniforms(seed, (uint32_t)(chain_offset + chain), (uint32_t)(sweep_offset + sweep_in_call), (uint32_t)m, 5, u);
+            zn = std_normal_from(u[0], u[1]);
+            zs = std_normal_from(u[2], u[3]);
+            ua = u[4];
+        }
+        hp = propose_noise_scale(sc->noise, sc->scale, prm, zn, zs);
+        s_uacc = ua;
+        // tighten the used extent: highest allocated column + 1
+        int hi = 0;
+        for (int w = P / 32 - 1; w >= 0; --w)
+            if (cv.colused[w]) { hi = w * 32 + 32 - __clz(cv.colused[w]); break; }
+        s_phi = hi;
+        if (hp.status) atomicOr(&sc->status, hp.status);
+    }
+    __syncthreads();
+    if (hp.status) return;
+    const int ph = s_phi;
+    const double sig2 = hp.noise + 1e-6;
+    const double c2 = sig2 * (double)m / hp.scale;
+    const double yy = sc->yy, cur_mll = sc->mll;
+
+    fill_B_lower(cv.Wk, cv.A, P, ph, c2);
+    for (int k = tid; k < ph; k += la::THREADS) cv.yv[k] = cv.b[k];
+    __syncthreads();
+    double quad = 0.0;
+    const double logdet = la::block_sweep<false>(cv.Wk, P, ph, cv.CK, cv.GK, cv.yv, &quad, s, &sc->status);
+    const double ldt2 = logdet - (double)ph * log(c2);
+    const double mll2 = mll_from(yy, quad, sig2, (double)n, ldt2);
+    const double log_alpha = hp.lqp + (mll2 - cur_mll);
+    const bool accept = log(s_uacc) <= fmin(log_alpha, 0.0);
+    if (tid == 0) {
+        if (trace) {
+            double* tr = trace + (((size_t)(chain * n_sweeps_call + sweep_in_call)) * (size_t)(m + 1) + m) * 3;
+            tr[0] = hp.lqp; tr[1] = mll2; tr[2] = accept ? 1.0 : 0.0;
+        }
+        sc->counters[3] += 1ull;
+        sc->p_hi = ph;
+    }
+    if (!accept) return;
+
+    // accepted: exact refresh of the running state (the reference refreshes K^-1 here too, :276-282)
+    fill_B_lower(cv.Binv, cv.A, P, ph, c2);
+    __syncthreads();
+    const double logdet_f = la::block_sweep<true>(cv.Binv, P, ph, cv.CK, cv.GK, nullptr, nullptr, s, &sc->status);
+    for (int k = ph + tid; k < P; k += la::THREADS) cv.Binv[(size_t)k * P + k] = 1.0 / c2;
+    __syncthreads();
+    const double q = matvec_w_q(cv.Binv, P, ph, cv.b, cv.w, s.red);
+    if (tid == 0) {
+        const double ldt = logdet_f - (double)ph * log(c2);
+        sc->noise = hp.noise; sc->scale = hp.scale; sc->sig = sig2; sc->c = c2;
+        sc->q = q; sc->ldt = ldt;
+        sc->mll = mll_from(yy, q, sig2, (double)n, ldt);
+        sc->counters[4] += 1ull;
+    }
+}
+
+// =====================================================================================================
+// read-out / export
+// =====================================================================================================
+__global__ void mcmc_read_kernel(WsLayout lay, const void* ws, double* noise, double* scale, double* mll,
+                                 uint32_t* status, uint64_t* counters, int32_t* p_used) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= lay.chains) return;
+    ChainView cv = chain_view(lay, const_cast<void*>(ws), c);
+    const ChainScalars* sc = cv.sc;
+    if (noise) noise[c] = sc->noise;
+    if (scale) scale[c] = sc->scale;
+    if (mll) mll[c] = sc->mll;
+    if (status) status[c] = sc->status;
+    if (counters) for (int k = 0; k < 8; ++k) counters[c * 8 + k] = sc->counters[k];
+    if (p_used) {
+        int cnt = 0;
+        for (int w = 0; w < lay.P / 32; ++w) cnt += __popc(cv.colused[w]);
+        p_used[c] = cnt;
+    }
+}
+
+__global__ void mcmc_export_kernel(WsLayout lay, const void* ws, int64_t chain, int32_t* A, double* Binv,
+                                   int32_t* colmap, uint32_t* bits) {
+    ChainView cv = chain_view(lay, const_cast<void*>(ws), chain);
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
+    const int64_t PP = lay.P * lay.P;
+    for (int64_t e = tid; e < PP; e += nth) {
+        if (A) A[e] = cv.A[e];
+        if (Binv) Binv[e] = cv.Binv[e];
+    }
+    if (colmap)
+        for (int64_t e = tid; e < lay.m * lay.L; e += nth) colmap[e] = cv.colmap[e] == NO_COL ? -1 : (int32_t)cv.colmap[e];
+    if (bits)
+        for (int64_t e = tid; e < lay.P * lay.wd; e += nth) bits[e] = cv.bits[e];
+}
+
+static int check_dims(const bark_mcmc_dims* dm) {
+    if (!dm) return 0;
+    if (dm->chains < 1 || dm->chains > 65535) return 0;
+    if (dm->n < 1 || dm->n > (1 << 22)) return 0;
+    if (dm->d < 1 || dm->d > 32767) return 0;
+    if (dm->m < 1 || dm->m > 4096) return 0;
+    if (dm->node_limit < 3 || dm->node_limit > 255) return 0;
+    if (dm->p_cap < 64 || dm->p_cap % 64 != 0 || dm->p_cap > 8192) return 0;
+    return 1;
+}
+
+}  // namespace bark
+
+using namespace bark;
+
+extern "C" {
+
+size_t bark_mcmc_workspace_bytes(const bark_mcmc_dims* dims) {
+    if (!check_dims(dims)) return 0;
+    return make_layout(*dims).total;
+}
+
+int bark_mcmc_init(const bark_mcmc_dims* dims, void* workspace, bark_nodes_soa forest, const double* X,
+                   const double* y, const double* bounds, const int32_t* feat_types, const double* noise,
+                   const double* scale, void* stream) {
+    BARK_CHECK_ARG(check_dims(dims), "bad dims (chains 1..65535, node_limit 3..255, p_cap multiple of 64 in 64..8192)");
+    BARK_CHECK_ARG(workspace && X && y && feat_types && noise && scale && forest.is_leaf, "null pointer");
+    const WsLayout lay = make_layout(*dims);
+    cudaStream_t st = (cudaStream_t)stream;
+    ws_setup_kernel<<<148, 256, 0, st>>>(lay, workspace, X, y, bounds, feat_types);
+    BARK_LAUNCH_CHECK();
+    const size_t smem = sizeof(la::Smem) + (size_t)lay.L * sizeof(WalkNode) + (size_t)(lay.d + lay.m + 2) * sizeof(int);
+    BARK_CHECK_ARG(smem <= 227 * 1024, "d + m too large for the init kernel's shared memory");
+    BARK_CUDA(cudaFuncSetAttribute(chain_init_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    chain_init_kernel<<<(unsigned)dims->chains, la::THREADS, smem, st>>>(lay, workspace, forest, noise, scale);
+    BARK_LAUNCH_CHECK();
+    return BARK_OK;
+}
+
+int bark_mcmc_sweeps(const bark_mcmc_dims* dims, void* workspace, bark_nodes_soa forest, const bark_params* params,
+                     int64_t n_sweeps, uint64_t seed, int64_t chain_offset, int64_t sweep_offset, const double* tape,
+                     double* trace, void* stream) {
+    BARK_CHECK_ARG(check_dims(dims), "bad dims");
+    BARK_CHECK_ARG(workspace && params && forest.is_leaf, "null pointer");
+    BARK_CHECK_ARG(n_sweeps >= 0, "n_sweeps < 0");
+    const WsLayout lay = make_layout(*dims);
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t smem = sweep_smem_bytes((int)lay.L, (int)lay.d, (int)lay.P, (int)lay.wd);
+    BARK_CHECK_ARG(smem <= 227 * 1024, "p_cap / n / d too large for the sweep kernel's shared memory");
+    BARK_CUDA(cudaFuncSetAttribute(sweep_trees_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    BARK_CUDA(cudaFuncSetAttribute(hyper_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(la::Smem)));
+    for (int64_t sidx = 0; sidx < n_sweeps; ++sidx) {
+        sweep_trees_kernel<<<(unsigned)dims->chains, SW_THREADS, smem, st>>>(lay, workspace, forest, *params, sidx, n_sweeps,
+                                                                           seed, chain_offset, sweep_offset, tape, trace);
+        hyper_kernel<<<(unsigned)dims->chains, la::THREADS, sizeof(la::Smem), st>>>(lay, workspace, *params, sidx, n_sweeps,
+                                                                                  seed, chain_offset, sweep_offset, tape, trace);
+    }
+    BARK_LAUNCH_CHECK();
+    return BARK_OK;
+}
+
+int bark_mcmc_read(const bark_mcmc_dims* dims, const void* workspace, double* noise, double* scale, double* mll,
+                   uint32_t* status, uint64_t* counters, int32_t* p_used, void* stream) {
+    BARK_CHECK_ARG(check_dims(dims) && workspace, "bad dims / null workspace");
+    const WsLayout lay = make_layout(*dims);
+    mcmc_read_kernel<<<(unsigned)ceil_div(dims->chains, 128), 128, 0, (cudaStream_t)stream>>>(
+        lay, workspace, noise, scale, mll, status, counters, p_used);
+    BARK_LAUNCH_CHECK();
+    return BARK_OK;
+}
+
+int bark_mcmc_export(const bark_mcmc_dims* dims, const void* workspace, int64_t chain, int32_t* A, double* Binv,
+                     int32_t* colmap, uint32_t* bits, void* stream) {
+    BARK_CHECK_ARG(check_dims(dims) && workspace, "bad dims / null workspace");
+    BARK_CHECK_ARG(chain >= 0 && chain < dims->chains, "chain out of range");
+    const WsLayout lay = make_layout(*dims);
+    mcmc_export_kernel<<<148, 256, 0, (cudaStream_t)stream>>>(lay, workspace, chain, A, Binv, colmap, bits);
+    BARK_LAUNCH_CHECK();
+    return BARK_OK;
+}
+
+}  // extern "C"

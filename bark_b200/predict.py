@@ -1,0 +1,77 @@
+"""Posterior predictive: `forest_predict` / `mixture_of_gaussians_as_normal`
+(src/bark/tree_kernels/tree_gps.py:80-131) on the GPU, in leaf space (csrc/predict.cu)."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import NamedTuple
+
+import numpy as np
+
+from . import _lib
+from .domain import unpack_domain
+from .forest import _as_device_f64, _ptr, _stream
+from .sampler import ChainState, raise_for_status
+
+
+class BARKModel(NamedTuple):  # src/bark/tree_kernels/tree_gps.py:14-17
+    forest: np.ndarray
+    noise: np.ndarray
+    scale: np.ndarray
+
+
+class PosteriorState:
+    """Per-sample leaf-space state (B^-1, w = B^-1 b, column maps) of all posterior samples, resident in HBM.
+    Build once, predict many candidate batches."""
+
+    def __init__(self, model, data, feat_types, d, p_cap=None, device=None):
+        forest, noise, scale = model
+        forest = np.ascontiguousarray(forest).reshape(-1, *forest.shape[-2:])
+        noise = np.asarray(noise, dtype=np.float64).reshape(-1)
+        scale = np.asarray(scale, dtype=np.float64).reshape(-1)
+        train_x, train_y = data
+        if p_cap is None:
+            leaves = int((forest["active"] & forest["is_leaf"]).sum(axis=(-1, -2)).max())
+            p_cap = max(64, ((leaves + 63) // 64) * 64)
+        bounds = np.zeros((d, 2))
+        self.state = ChainState(forest, noise, scale, train_x, train_y, bounds, feat_types, p_cap=p_cap, device=device)
+        self.num_samples = forest.shape[0]
+
+    def check(self):
+        raise_for_status(self.state.read()["status"].cpu().numpy())
+
+    def predict_device(self, cand_dev, mode=0, y_mean=0.0, y_std=1.0, add_noise=False):
+        """cand_dev (n_c, d) f64 CUDA tensor -> (mu, var) CUDA tensors: (S, n_c) for mode 0, (n_c,) for mode 1."""
+        torch = _lib.require_cuda()
+        st = self.state
+        n_c = cand_dev.shape[0]
+        shape = (self.num_samples, n_c) if mode == 0 else (n_c,)
+        mu = torch.empty(shape, dtype=torch.float64, device=st.device)
+        var = torch.empty(shape, dtype=torch.float64, device=st.device)
+        nbytes = int(st.lib.bark_predict_scratch_bytes(C.byref(st.dims), n_c))
+        scratch = torch.empty(max(nbytes, 8), dtype=torch.uint8, device=st.device)
+        _lib.check(st.lib.bark_predict(C.byref(st.dims), _ptr(st.ws), st.dforest.soa(), _ptr(cand_dev), n_c, int(mode),
+                                       float(y_mean), float(y_std), int(bool(add_noise)), _ptr(mu), _ptr(var),
+                                       _ptr(scratch), _stream()))
+        return mu, var
+
+
+def forest_predict(model, data, candidates: np.ndarray, domain, diag: bool = True):
+    """Per-sample posterior mean and variance at `candidates` (src/bark/tree_kernels/tree_gps.py:80-113).
+    Leading sample dims of the model are flattened; returns (mu (S_tot, n_c), var (S_tot, n_c))."""
+    if not diag:
+        raise NotImplementedError("only diag=True is served by the GPU path (the reference's callers use diag=True)")
+    _lib.require_cuda()
+    _, feat_types = unpack_domain(domain)
+    candidates = np.ascontiguousarray(candidates, dtype=np.float64)
+    ps = PosteriorState(model, data, feat_types, candidates.shape[1])
+    mu, var = ps.predict_device(_as_device_f64(candidates, ps.state.device), mode=0)
+    ps.check()
+    return mu.cpu().numpy(), var.cpu().numpy()
+
+
+def mixture_of_gaussians_as_normal(mu: np.ndarray, var: np.ndarray):
+    """Mean and variance of an equal-weight mixture of Gaussians (src/bark/tree_kernels/tree_gps.py:116-131).
+    (Host version for arrays already on the host; `PosteriorState.predict_device(mode=1)` fuses it on the GPU.)"""
+    mu_y = np.mean(mu, axis=0)
+    var_y = np.mean(var + mu**2, axis=0) - mu_y**2
+    return mu_y, var_y

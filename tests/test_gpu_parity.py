@@ -1,0 +1,332 @@
+"""GPU parity tests proper: the CUDA path (through the C ABI) against the oracle and the committed golden
+fixtures.  Run with `-m gpu` on a B200."""
+import os
+
+import numpy as np
+import pytest
+
+import bark_b200 as B
+from bark_b200 import sampler as S
+from oracle import bark_oracle as O
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def rec(a):
+    return np.ascontiguousarray(a).view(O.NODE_RECORD_DTYPE).reshape(a.shape[:-1] + (a.shape[-1] // 26,))
+
+
+def load(name):
+    return np.load(os.path.join(G, name))
+
+
+def random_forests(n_forests, m, bounds, ft, sweeps=30, seed=0):
+    """Forests with realistic structure: run the oracle's prior-like proposal chain (accept everything valid)."""
+    rng = np.random.default_rng(seed)
+    cdf = np.cumsum([0.5, 0.1, 0.4])
+    out = np.tile(O.create_empty_forest(m), (n_forests, 1, 1))
+    for f in out:
+        for _ in range(sweeps):
+            for t in range(m):
+                tape = rng.random(5)
+                new, lqp, st = O.get_tree_proposal(f[t], bounds, ft, 0.95, 2.0, cdf, tape, 0)
+                if np.isfinite(lqp):
+                    f[t] = new
+    return out
+
+
+# ----------------------------------------------------------------------------------------- a1 codec
+def test_codec_roundtrip_lossless():
+    import torch
+    from bark_b200.forest import DeviceForest
+    rng = np.random.default_rng(1)
+    raw = rng.integers(0, 256, size=(3, 7, 100, 26), dtype=np.uint8)  # arbitrary bytes incl. NaN thresholds
+    nodes = raw.view(O.NODE_RECORD_DTYPE).reshape(3, 7, 100)
+    back = DeviceForest.from_numpy(nodes).to_numpy()
+    assert back.tobytes() == nodes.tobytes()
+    df = DeviceForest.from_numpy(nodes)
+    assert np.array_equal(df.parent.cpu().numpy().view(np.uint32).reshape(3, 7, 100), nodes["parent"])
+    assert np.array_equal(df.threshold.cpu().numpy().view(np.uint32).reshape(3, 7, 100), nodes["threshold"].view(np.uint32))
+    empty = B.create_empty_forest(5)
+    assert DeviceForest.from_numpy(empty).to_numpy().tobytes() == empty.tobytes()
+    torch.cuda.synchronize()
+
+
+# ----------------------------------------------------------------------------------------- a2 traversal
+def test_traversal_kat():
+    k = load("kat.npz")
+    ft = np.array([2])
+    assert B.pass_through_forest(rec(k["kat_tree"]).reshape(1, -1), k["x20"], ft)[:, 0].tolist() == [3] * 5 + [4] * 5 + [2] * 10
+    assert B.pass_through_forest(rec(k["t_thr"]).reshape(1, -1), k["xb"], ft)[:, 0].tolist() == [1, 1, 2, 1]
+    assert B.pass_through_forest(rec(k["t_cat"]).reshape(1, -1), k["xc"], np.array([0]))[:, 0].tolist() == [2, 1, 1, 2, 1]
+
+
+@pytest.mark.parametrize("tag", ["cont", "mixed"])
+def test_traversal_golden(tag):
+    s, g = load(f"sampler_{tag}.npz"), load(f"functions_{tag}.npz")
+    ns = rec(s["node_samples"])
+    forests = ns.reshape(-1, *ns.shape[-2:])
+    got = B.pass_through_forest(forests, g["Xp"], s["feat_types"])
+    assert got.dtype == np.uint32 and np.array_equal(got, g["leaves"])  # bit-exact vs the reference's own output
+
+
+@pytest.mark.parametrize("n,m,dims", [(1, 1, (1, 0)), (257, 33, (3, 2)), (2000, 200, (10, 0)), (500, 100, (6, 4))])
+def test_traversal_random_vs_oracle(n, m, dims):
+    dim, cat = dims
+    fn = O.TreeFunction(dim=dim, cat_dim=cat, num_cat=5, m=2, function_seed=3)
+    forests = random_forests(2, m, fn.bounds, fn.feat_types, sweeps=12, seed=n)
+    X = fn.sample_inputs(n, np.random.default_rng(n))
+    # put points exactly on, just above and just below f32 thresholds; signed zeros
+    f0 = forests[0]
+    k = 0
+    for t in range(m):
+        for nd in f0[t]:
+            if nd["active"] and not nd["is_leaf"] and fn.feat_types[nd["feature_idx"]] == 2 and k + 3 <= n:
+                thr = float(nd["threshold"])
+                X[k, nd["feature_idx"]], X[k + 1, nd["feature_idx"]], X[k + 2, nd["feature_idx"]] = \
+                    thr, np.nextafter(thr, 2.0), np.nextafter(thr, -2.0)
+                k += 3
+    if n > 3:
+        X[-1, 0] = -0.0
+    want = np.stack([O.pass_through_forest(f, X, fn.feat_types) for f in forests])
+    got = B.pass_through_forest(forests, X, fn.feat_types)
+    assert np.array_equal(got, want)
+
+
+def test_traversal_empty_inputs():
+    f = B.create_empty_forest(3)
+    assert B.pass_through_forest(f, np.zeros((0, 2)), [2, 2]).shape == (0, 3)
+    out = B.pass_through_forest(f, np.zeros((5, 2)), [2, 2])
+    assert out.shape == (5, 3) and not out.any()  # root-only trees: every point in slot 0
+
+
+# ----------------------------------------------------------------------------------------- a3/a4 Gram
+@pytest.mark.parametrize("tag", ["cont", "mixed"])
+def test_gram_golden_bit_exact(tag):
+    s, g = load(f"sampler_{tag}.npz"), load(f"functions_{tag}.npz")
+    ns = rec(s["node_samples"])
+    forests = ns.reshape(-1, *ns.shape[-2:])
+    X, ft = s["X"], s["feat_types"]
+    assert np.array_equal(B.batched_forest_gram_matrix(forests, X, X, ft), g["gram"])
+    assert np.array_equal(B.batched_forest_gram_matrix(forests, g["Xp"], X, ft), g["gram_cross"])
+    assert np.allclose(B.batched_forest_gram_matrix_no_null(forests, X, X, ft), g["gram_nonull"], rtol=1e-15, atol=0)
+    k = load("kat.npz")
+    K = B.forest_gram_matrix(rec(k["kat_tree"]).reshape(1, -1), k["x20"], k["x20"], np.array([2]))
+    assert np.array_equal(K, k["kat_K"]) and K.sum() == 150
+    for i in range(6):
+        assert np.array_equal(B.get_leaf_vectors(forests[0][i], X, ft), g[f"leafvec{i}"])
+
+
+@pytest.mark.parametrize("n,n2,m", [(65, 1, 3), (300, 129, 51), (700, 700, 201)])
+def test_gram_counts_random(n, n2, m):
+    fn = O.TreeFunction(dim=4, cat_dim=2, num_cat=5, m=2, function_seed=3)
+    forests = random_forests(2, m, fn.bounds, fn.feat_types, sweeps=10, seed=m)
+    rng = np.random.default_rng(m)
+    X1, X2 = fn.sample_inputs(n, rng), fn.sample_inputs(n2, rng)
+    got = B.forest_gram_counts(forests, X1, X2, fn.feat_types)
+    want = np.stack([O.forest_gram_counts(f, X1, X2, fn.feat_types) for f in forests])
+    assert got.dtype == np.int32 and np.array_equal(got, want)
+    # K0 = (1/m)*count: multiply by the rounded reciprocal (differs from count/m in the last ulp)
+    K0 = B.batched_forest_gram_matrix(forests, X1, X2, fn.feat_types)
+    assert np.array_equal(K0, (1 / m) * want.astype(np.float64))
+
+
+def test_gram_kernel_matrix_bit_exact():
+    import torch
+    from bark_b200.forest import gram_to_kernel_device
+    rng = np.random.default_rng(0)
+    m = 51
+    cnt = rng.integers(0, m + 1, size=(3, 40, 40)).astype(np.int32)
+    scale, noise = rng.random(3) + 0.5, rng.random(3) * 0.3
+    K = gram_to_kernel_device(torch.from_numpy(cnt).cuda(), m, torch.from_numpy(scale).cuda(), torch.from_numpy(noise).cuda())
+    want = np.stack([scale[i] * ((1 / m) * cnt[i].astype(np.float64)) + (1e-6 + noise[i]) * np.eye(40) for i in range(3)])
+    assert np.array_equal(K.cpu().numpy(), want)
+
+
+# ----------------------------------------------------------------------------------------- a5 MLL
+@pytest.mark.parametrize("tag", ["cont", "mixed"])
+def test_mll_golden(tag):
+    s, g = load(f"sampler_{tag}.npz"), load(f"functions_{tag}.npz")
+    ns = rec(s["node_samples"])
+    forests = ns.reshape(-1, *ns.shape[-2:])
+    got = B.forest_mll(forests, s["noise_samples"].reshape(-1), s["scale_samples"].reshape(-1), s["X"], s["y"], s["feat_types"])
+    assert np.allclose(got, g["mll"], rtol=1e-9, atol=0)  # north_star tolerance: 1e-9 relative
+    assert np.abs(got / g["mll"] - 1).max() < 1e-11
+
+
+@pytest.mark.parametrize("n", [1, 63, 64, 65, 250, 517])
+def test_mll_batched_random_spd(n):
+    import torch
+    from bark_b200.mll import mll_batched_device
+    rng = np.random.default_rng(n)
+    b = 5
+    Z = (rng.random((b, n, max(n // 3, 2))) < 0.3).astype(np.float64)
+    K = np.einsum("bik,bjk->bij", Z, Z) / 7 + (0.05 + rng.random((b, 1, 1))) * np.eye(n)
+    y = rng.standard_normal(n)
+    val, ld, quad, st = mll_batched_device(torch.from_numpy(K.copy()).cuda(), torch.from_numpy(y).cuda())
+    assert int(st.max()) == 0
+    for i in range(b):
+        want_ld = np.linalg.slogdet(K[i])[1]
+        want_q = y @ np.linalg.solve(K[i], y)
+        assert ld[i].item() == pytest.approx(want_ld, rel=1e-11, abs=1e-11)
+        assert quad[i].item() == pytest.approx(want_q, rel=1e-11)
+        assert val[i].item() == pytest.approx(O.mll_cholesky(K[i], y), rel=1e-10, abs=1e-11)
+
+
+def test_mll_flags_non_spd():
+    import torch
+    from bark_b200.mll import mll_batched_device
+    K = -np.eye(8)[None]
+    _, _, _, st = mll_batched_device(torch.from_numpy(K.copy()).cuda(), torch.zeros(8, dtype=torch.float64).cuda())
+    assert int(st[0]) & 8
+
+
+# ----------------------------------------------------------------------------------------- a8-a13 MCMC replay
+def replay_case(n, dim, cat, m, chains, warm, ns, sps, seed, **pkw):
+    X, y, bounds, ft, _ = O.synthetic_problem(n, dim=dim, cat_dim=cat, num_cat=4, m_true=10, seed=seed)
+    p = O.BARKTrainParams(warmup_steps=warm, num_samples=ns, steps_per_sample=sps, num_chains=chains, **pkw)
+    sweeps = warm + ns * sps
+    tape = O.make_tape(np.random.default_rng(seed + 100), chains, sweeps, m)
+    trace_o = np.zeros((chains, sweeps, m + 1, 3))
+    f0 = np.tile(O.create_empty_forest(m), (chains, 1, 1))
+    noise0, scale0 = np.full(chains, 0.1), np.full(chains, 1.0)
+    want = O.run_bark_sampler((f0.copy(), noise0, scale0), (X, y), bounds, ft, p, tape=tape, trace=trace_o)
+    pg = B.BARKTrainParams(warmup_steps=warm, num_samples=ns, steps_per_sample=sps, num_chains=chains, **pkw)
+    got = B.run_bark_sampler((f0.copy(), noise0, scale0), (X, y), (bounds, ft), pg, tape=tape, return_trace=True,
+                             return_info=True)
+    return want, trace_o, got, (X, y, bounds, ft)
+
+
+@pytest.mark.parametrize("case", [
+    dict(n=50, dim=5, cat=0, m=50, chains=1, warm=10, ns=2, sps=5, seed=0),      # BASELINE config 1 shape
+    dict(n=60, dim=3, cat=2, m=12, chains=3, warm=8, ns=2, sps=4, seed=1),       # mixed categorical
+    dict(n=130, dim=4, cat=0, m=20, chains=2, warm=6, ns=1, sps=4, seed=2),
+    dict(n=40, dim=2, cat=1, m=8, chains=2, warm=5, ns=2, sps=3, seed=3, sample_scale=True),
+    dict(n=40, dim=2, cat=1, m=8, chains=2, warm=5, ns=2, sps=3, seed=4, sample_scale=True, use_softplus_transform=False),
+])
+def test_mcmc_replay_matches_oracle(case):
+    """Same pre-drawn random numbers -> same trajectory: every proposal's log q/prior ratio, proposed log-MLL and
+    accept bit, and the sampled forests byte for byte."""
+    want, trace_o, got, _ = replay_case(**case)
+    ns_g, noise_g, scale_g, trace_g, info = got
+    lq_o, lq_g = trace_o[..., 0], trace_g[..., 0]
+    assert np.array_equal(np.isfinite(lq_o), np.isfinite(lq_g))
+    fin = np.isfinite(lq_o)
+    assert np.allclose(lq_g[fin], lq_o[fin], rtol=0, atol=1e-12)
+    flips = trace_o[..., 2] != trace_g[..., 2]
+    assert not flips.any(), f"{flips.sum()} accept decisions differ"
+    # proposed log-MLL of every valid proposal: 1e-9 relative (north_star)
+    rel = np.abs(trace_g[..., 1][fin] - trace_o[..., 1][fin]) / np.maximum(np.abs(trace_o[..., 1][fin]), 1e-300)
+    assert rel.max() < 1e-9, rel.max()
+    assert ns_g.tobytes() == want[0].tobytes()
+    assert np.allclose(noise_g, want[1], rtol=1e-12, atol=0) and np.allclose(scale_g, want[2], rtol=1e-12, atol=0)
+    assert int(info["tree_proposals"].sum()) == trace_o.shape[0] * trace_o.shape[1] * (trace_o.shape[2] - 1)
+    assert int(info["accepted"].sum()) == int(trace_o[:, :, :-1, 2].sum())
+    assert int(info["hyper_accepted"].sum()) == int(trace_o[:, :, -1, 2].sum())
+
+
+def test_mcmc_state_consistency_after_sweeps():
+    """Leaf-space state kept by the kernels == state recomputed from the final forest by the oracle."""
+    X, y, bounds, ft, _ = O.synthetic_problem(90, dim=3, cat_dim=1, num_cat=4, m_true=10, seed=5)
+    chains, m = 2, 16
+    f0 = np.tile(O.create_empty_forest(m), (chains, 1, 1))
+    st = S.ChainState(f0, np.full(chains, 0.1), np.full(chains, 1.0), X, y, bounds, ft)
+    p = B.BARKTrainParams(num_chains=chains)
+    st.sweeps(p, 25, seed=123)
+    r = st.read()
+    assert int(r["status"].max()) == 0
+    forest = st.dforest.to_numpy()
+    for c in range(chains):
+        ex = st.export(c)
+        leaves = O.pass_through_forest(forest[c], X, ft)
+        cm = ex["colmap"]
+        P = st.p_cap
+        Z = np.zeros((X.shape[0], P))
+        for t in range(m):
+            for sl in range(100):
+                is_leaf = forest[c, t, sl]["active"] and forest[c, t, sl]["is_leaf"]
+                assert (cm[t, sl] >= 0) == bool(is_leaf)
+            Z[np.arange(X.shape[0]), cm[t, leaves[:, t]]] = 1
+        assert np.array_equal(ex["A"], (Z.T @ Z).astype(np.int32))
+        bits = np.unpackbits(ex["bits"].view(np.uint8), axis=1, bitorder="little")[:, :X.shape[0]]
+        assert np.array_equal(bits, Z.T.astype(np.uint8))
+        noise, scale = r["noise"][c].item(), r["scale"][c].item()
+        cc = (noise + 1e-6) * m / scale
+        Bm = cc * np.eye(P) + Z.T @ Z
+        assert np.abs(ex["Binv"] @ Bm - np.eye(P)).max() < 1e-9
+        K = O.kernel_matrix(forest[c], X, ft, noise, scale)
+        assert r["mll"][c].item() == pytest.approx(O.mll_from_kernel(K, y), rel=1e-9)
+        assert int(r["p_used"][c]) == int((forest[c]["active"] & forest[c]["is_leaf"]).sum())
+
+
+def test_mcmc_philox_run_statistics():
+    """Free-running (Philox) chains: valid structure, finite MLL equal to the refactorised one, sane acceptance."""
+    X, y, bounds, ft, _ = O.synthetic_problem(120, dim=4, cat_dim=0, m_true=10, seed=7)
+    chains, m = 8, 20
+    p = B.BARKTrainParams(warmup_steps=30, num_samples=3, steps_per_sample=5, num_chains=chains)
+    f0 = np.tile(O.create_empty_forest(m), (chains, 1, 1))
+    ns, noise, scale, info = B.run_bark_sampler((f0, np.full(chains, 0.1), np.full(chains, 1.0)), (X, y), (bounds, ft), p,
+                                                seed=42, return_info=True)
+    assert ns.shape == (chains, 3, m, 100) and noise.shape == (chains, 3)
+    ns2, noise2, _, _ = B.run_bark_sampler((f0, np.full(chains, 0.1), np.full(chains, 1.0)), (X, y), (bounds, ft), p,
+                                           seed=42, return_info=True)
+    assert ns.tobytes() == ns2.tobytes() and np.array_equal(noise, noise2)  # deterministic given the seed
+    acc = info["accepted"].sum() / info["tree_proposals"].sum()
+    assert 0.05 < acc < 0.9
+    assert len({ns[c].tobytes() for c in range(chains)}) == chains  # chains use distinct streams
+    for c in range(chains):
+        K = O.kernel_matrix(ns[c, -1], X, ft, noise[c, -1], scale[c, -1])
+        assert info["mll"][c] == pytest.approx(O.mll_from_kernel(K, y), rel=1e-9)
+        for t in range(m):  # structural invariants of every sampled tree
+            tr = ns[c, -1, t]
+            for i in np.flatnonzero(tr["active"] & (1 - tr["is_leaf"])):
+                assert tr[tr[i]["left"]]["active"] and tr[tr[i]["right"]]["active"]
+                assert tr[tr[i]["left"]]["parent"] == i and tr[tr[i]["left"]]["depth"] == tr[i]["depth"] + 1
+
+
+def test_mcmc_error_conventions():
+    X, y, bounds, ft, _ = O.synthetic_problem(30, dim=2, m_true=5, seed=1)
+    f0 = np.tile(O.create_empty_forest(4), (1, 1, 1))
+    p = B.BARKTrainParams(warmup_steps=1, num_samples=1, steps_per_sample=1, num_chains=1,
+                          use_softplus_transform=False, sample_scale=False)
+    with pytest.raises(NotImplementedError):
+        B.run_bark_sampler((f0, [0.1], [1.0]), (X, y), (bounds, ft), p, seed=1)
+    # tree container overflow: node_limit 3 cannot hold a second grow
+    small = np.zeros((1, 4, 3), dtype=O.NODE_RECORD_DTYPE)
+    small[:, :, 0] = (1, 0, 0, 0, 0, 0xFFFFFFFF, 0, 1)
+    p2 = B.BARKTrainParams(warmup_steps=40, num_samples=1, steps_per_sample=1, num_chains=1, proposal_weights=(1.0, 0.0, 0.0))
+    with pytest.raises(OverflowError):
+        B.run_bark_sampler((small, [0.1], [1.0]), (X, y), (bounds, ft), p2, seed=1)
+
+
+# ----------------------------------------------------------------------------------------- a14-a15 predict
+@pytest.mark.parametrize("tag", ["cont", "mixed"])
+def test_predict_golden(tag):
+    s, g = load(f"sampler_{tag}.npz"), load(f"functions_{tag}.npz")
+    model = (rec(s["node_samples"]), s["noise_samples"], s["scale_samples"])
+    mu, var = B.forest_predict(model, (s["X"], s["y"]), g["Xp"], (s["bounds"], s["feat_types"]))
+    assert mu.shape == g["pred_mu"].shape
+    assert np.allclose(mu, g["pred_mu"], rtol=1e-9, atol=1e-11)
+    assert np.allclose(var, g["pred_var"], rtol=1e-8, atol=1e-11)
+    mm, mv = B.mixture_of_gaussians_as_normal(mu, var)
+    assert np.allclose(mm, g["mix_mu"], rtol=1e-9, atol=1e-11) and np.allclose(mv, g["mix_var"], rtol=1e-8, atol=1e-11)
+
+
+def test_surrogate_fit_predict_end_to_end():
+    X, y, bounds, ft, scaler = O.synthetic_problem(80, dim=3, cat_dim=1, num_cat=4, m_true=10, seed=9)
+    y_raw = y * 2.5 + 1.0
+    sur = B.BARKSurrogate((bounds, ft), warmup_steps=20, num_samples=3, steps_per_sample=4, num_trees=10, num_chains=2, seed=5)
+    sur.fit(X, y_raw)
+    assert sur.forest.shape == (2, 3, 10, 100) and sur.is_fitted
+    Xc = X[:17]
+    mu, sd = sur.predict(Xc)
+    mu_b, sd_b = sur.predict(Xc, batched=True)
+    assert mu.shape == (17, 1) and mu_b.shape == (6, 17, 1)
+    sc = O.Standardize(); sc.mean, sc.std = sur.scaler.mean, sur.scaler.std
+    want_mu, want_sd = O.surrogate_predict(sur.model_as_tuple(), sur.train_data, Xc, ft, sc)
+    assert np.allclose(mu, want_mu, rtol=1e-9, atol=1e-10) and np.allclose(sd, want_sd, rtol=1e-8, atol=1e-10)
+    want_mu_b, want_sd_b = O.surrogate_predict(sur.model_as_tuple(), sur.train_data, Xc, ft, sc, batched=True)
+    assert np.allclose(mu_b, want_mu_b, rtol=1e-9, atol=1e-10) and np.allclose(sd_b, want_sd_b, rtol=1e-8, atol=1e-10)
+    sur.fit(X, y_raw)  # warm start: continues from the last sample with warmup 0 (surrogates/bark.py:131-141)
+    assert sur.bark_params.warmup_steps == 0 and sur.forest.shape == (2, 3, 10, 100)

@@ -1,0 +1,112 @@
+"""CPU-side checks of the product package: C-ABI library loads and exports every symbol the header declares,
+host logic, and 'no silent fallback' behaviour.  No GPU compute here."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import bark_b200
+from bark_b200 import _build, _lib, domain, sampler
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    _build.build()
+    return _lib.load()
+
+
+def header_functions():
+    src = open(os.path.join(ROOT, "include", "bark_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(bark_[a-z_0-9]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol(lib):
+    names = header_functions()
+    assert len(names) >= 15
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/bark_b200.h but not exported"
+        assert n in _lib.SIGNATURES, f"{n} has no ctypes signature"
+    assert lib.bark_abi_version() == 1
+
+
+def test_struct_layouts_match_header():
+    assert ctypes.sizeof(_lib.NodesSoA) == 8 * 8
+    assert ctypes.sizeof(_lib.McmcDims) == 6 * 8
+    assert ctypes.sizeof(_lib.Params) == 7 * 8 + 2 * 4
+    assert bark_b200.NODE_RECORD_DTYPE.itemsize == 26
+
+
+def test_workspace_sizes_and_argument_validation(lib):
+    d = _lib.McmcDims(64, 2000, 10, 200, 100, 1600)
+    nbytes = lib.bark_mcmc_workspace_bytes(ctypes.byref(d))
+    assert 1e9 < nbytes < 8e9  # fits 180 GB HBM with room for 50x more chains
+    bad = _lib.McmcDims(64, 2000, 10, 200, 100, 1601)  # p_cap not a multiple of 64
+    assert lib.bark_mcmc_workspace_bytes(ctypes.byref(bad)) == 0
+    assert lib.bark_mll_workspace_bytes(16, 250) > 0
+    # invalid arguments are rejected before any CUDA call
+    rc = lib.bark_gram_counts(None, None, 1, 4, 4, 3, None, None)
+    assert rc == 1 and b"null" in lib.bark_last_error()
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(_lib.BarkError):
+        bark_b200.pass_through_forest(bark_b200.create_empty_forest(2), np.zeros((3, 1)), [2])
+    with pytest.raises(_lib.BarkError):
+        p = bark_b200.BARKTrainParams(num_chains=1)
+        bark_b200.run_bark_sampler((bark_b200.create_empty_forest(2)[None], [0.1], [1.0]),
+                                   (np.zeros((3, 1)), np.zeros((3, 1))), (np.array([[0.0, 1.0]]), np.array([2])), p)
+
+
+def test_product_package_never_imports_oracle():
+    for root, _, files in os.walk(os.path.join(ROOT, "bark_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(root, f)).read()
+                assert "import oracle" not in txt and "from oracle" not in txt, f
+
+
+def test_empty_forest_and_params():
+    f = bark_b200.create_empty_forest(4)
+    assert f.shape == (4, 100) and f[2, 0]["parent"] == 0xFFFFFFFF and f[2, 0]["active"] == 1 and f[2, 1]["active"] == 0
+    p = bark_b200.BARKTrainParams()
+    assert (p.warmup_steps, p.num_samples, p.steps_per_sample, p.num_chains) == (50, 5, 10, 1)
+    c = p.to_c()
+    assert list(c.proposal_weights) == [0.25, 0.25, 0.5] and c.use_softplus_transform == 1 and c.sample_scale == 0
+    assert sampler.default_p_cap(200, 100) == 1600 and sampler.default_p_cap(50, 100) == 448
+    assert sampler.default_p_cap(2, 100) % 64 == 0
+
+
+def test_status_to_exception_mapping():
+    with pytest.raises(OverflowError, match="tree container"):
+        sampler.raise_for_status(np.array([0, 1]))
+    with pytest.raises(NotImplementedError):
+        sampler.raise_for_status(np.array([2]))
+    with pytest.raises(_lib.BarkError):
+        sampler.raise_for_status(np.array([4]))
+    sampler.raise_for_status(np.array([0, 0]))
+
+
+def test_domain_adapters():
+    dom = domain.Domain(inputs=domain.Inputs([
+        domain.ContinuousInput("x0", (0.0, 1.0)), domain.DiscreteInput("i0", [1, 2, 3, 7]),
+        domain.CategoricalInput("c0", ["a", "b", "c"])]))
+    bounds, ft = domain.unpack_domain(dom)
+    assert bounds.tolist() == [[0.0, 1.0], [1.0, 7.0], [0.0, 7.0]] and ft.tolist() == [2, 1, 0]
+    b2, f2 = domain.unpack_domain((bounds, ft))
+    assert np.array_equal(b2, bounds) and np.array_equal(f2, ft)
+    assert domain.get_feature_bounds(dom.inputs.get()[2], "ordinal") == [0, 1, 2]
+
+
+def test_mixture_moments_host():
+    rng = np.random.default_rng(0)
+    mu, var = rng.standard_normal((6, 9)), rng.random((6, 9))
+    m, v = bark_b200.mixture_of_gaussians_as_normal(mu, var)
+    assert np.allclose(m, mu.mean(0)) and np.allclose(v, (var + mu**2).mean(0) - mu.mean(0) ** 2)
