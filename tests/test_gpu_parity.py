@@ -213,7 +213,12 @@ def test_mcmc_replay_matches_oracle(case):
     lq_o, lq_g = trace_o[..., 0], trace_g[..., 0]
     assert np.array_equal(np.isfinite(lq_o), np.isfinite(lq_g))
     fin = np.isfinite(lq_o)
-    assert np.allclose(lq_g[fin], lq_o[fin], rtol=0, atol=1e-12)
+    tree = fin.copy(); tree[..., -1] = False
+    assert np.allclose(lq_g[tree], lq_o[tree], rtol=0, atol=1e-12)
+    # hyper step: with sample_scale the reference's log_q divides a squared 1e-8-sized difference by 1e-16
+    # (noise_scale_proposals.py:113-121), which amplifies last-ulp libm differences to ~1e-8
+    hyp_tol = 1e-6 if case.get("sample_scale") else 1e-12
+    assert np.allclose(lq_g[..., -1], lq_o[..., -1], rtol=hyp_tol, atol=hyp_tol)
     flips = trace_o[..., 2] != trace_g[..., 2]
     assert not flips.any(), f"{flips.sum()} accept decisions differ"
     # proposed log-MLL of every valid proposal: 1e-9 relative (north_star)
