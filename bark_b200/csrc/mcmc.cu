@@ -13,6 +13,7 @@
 // prune, where Binv v = e_b - c Binv[:,b]) plus O(P) dot products (2x2 capacitance matrix).  On accept the
 // state takes a symmetric rank-2 update.  One CTA owns one chain for the whole sweep.
 #include <algorithm>
+#include <vector>
 
 #include "common.cuh"
 #include "forest_device.cuh"
@@ -205,7 +206,7 @@ chain_init_kernel(WsLayout lay, void* ws, bark_nodes_soa forest, const double* _
         sc->ldt = ldt;
         sc->yy = yy;
         sc->mll = mll_from(yy, q, sig, (double)n, ldt);
-        for (int k = 0; k < 8; ++k) sc->counters[k] = 0ull;
+        for (int k = 0; k < 16; ++k) sc->counters[k] = 0ull;
         sc->p_hi = ptot;
     }
 }
@@ -271,7 +272,8 @@ sweep_trees_kernel(WsLayout lay, void* ws, bark_nodes_soa forest, bark_params pr
         ctl->q = sc->q; ctl->ldt = sc->ldt; ctl->mll = sc->mll; ctl->p_hi = sc->p_hi;
     }
     for (int e = tid; e < d; e += SW_THREADS) ftc[e] = sv.ft[e];
-    unsigned long long n_valid = 0, n_acc = 0, n_acc_move[3] = {0, 0, 0};  // thread 0 only
+    unsigned long long n_valid = 0, n_acc = 0, n_acc_move[3] = {0, 0, 0}, n_valid_move[3] = {0, 0, 0};  // thread 0 only
+    unsigned long long blk_eval = 0, blk_upd = 0, cols_scanned = 0;
 
     const uint32_t g_chain = (uint32_t)(chain_offset + chain), g_sweep = (uint32_t)(sweep_offset + sweep_in_call);
     const size_t tape_base = tape ? ((size_t)(chain * n_sweeps_call + sweep_in_call)) * (size_t)(m * TAPE_PER_TREE + TAPE_PER_HYPER) : 0;
@@ -431,7 +433,14 @@ sweep_trees_kernel(WsLayout lay, void* ws, bark_nodes_soa forest, bark_params pr
                     trace_base[t * 3 + 1] = new_mll;
                     trace_base[t * 3 + 2] = accept ? 1.0 : 0.0;
                 }
-                n_valid += p.valid ? 1 : 0;
+                if (p.valid) {
+                    ++n_valid;
+                    ++n_valid_move[p.move];
+                    const unsigned long long nb64 = (unsigned long long)(pe64 / 64);
+                    if (p.move != MOVE_PRUNE) blk_eval += nb64 * nb64;
+                    if (accept) blk_upd += nb64 * nb64;
+                    cols_scanned += (unsigned long long)pe64;
+                }
             }
         }
 
@@ -541,6 +550,12 @@ sweep_trees_kernel(WsLayout lay, void* ws, bark_nodes_soa forest, bark_params pr
         sc->counters[5] += n_acc_move[0];
         sc->counters[6] += n_acc_move[1];
         sc->counters[7] += n_acc_move[2];
+        sc->counters[8] += n_valid_move[0];
+        sc->counters[9] += n_valid_move[1];
+        sc->counters[10] += n_valid_move[2];
+        sc->counters[11] += blk_eval;      // sum over matvec evaluations of (extent/64)^2
+        sc->counters[12] += blk_upd;       // sum over accepted updates of (extent/64)^2
+        sc->counters[13] += cols_scanned;  // leaf-bitset columns scanned for v = Z^T u
     }
 }
 
@@ -639,7 +654,7 @@ __global__ void mcmc_read_kernel(WsLayout lay, const void* ws, double* noise, do
     if (scale) scale[c] = sc->scale;
     if (mll) mll[c] = sc->mll;
     if (status) status[c] = sc->status;
-    if (counters) for (int k = 0; k < 8; ++k) counters[c * 8 + k] = sc->counters[k];
+    if (counters) for (int k = 0; k < 16; ++k) counters[c * 16 + k] = sc->counters[k];
     if (p_used) {
         int cnt = 0;
         for (int w = 0; w < lay.P / 32; ++w) cnt += __popc(cv.colused[w]);
@@ -720,6 +735,44 @@ int bark_mcmc_sweeps(const bark_mcmc_dims* dims, void* workspace, bark_nodes_soa
                                                                                   seed, chain_offset, sweep_offset, tape, trace);
     }
     BARK_LAUNCH_CHECK();
+    return BARK_OK;
+}
+
+int bark_mcmc_sweeps_timed(const bark_mcmc_dims* dims, void* workspace, bark_nodes_soa forest, const bark_params* params,
+                           int64_t n_sweeps, uint64_t seed, int64_t chain_offset, int64_t sweep_offset,
+                           float* ms_trees_host, float* ms_hyper_host, void* stream) {
+    BARK_CHECK_ARG(check_dims(dims), "bad dims");
+    BARK_CHECK_ARG(workspace && params && forest.is_leaf && ms_trees_host && ms_hyper_host, "null pointer");
+    BARK_CHECK_ARG(n_sweeps >= 1 && n_sweeps <= 4096, "n_sweeps out of range (1..4096)");
+    const WsLayout lay = make_layout(*dims);
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t smem = sweep_smem_bytes((int)lay.L, (int)lay.d, (int)lay.P, (int)lay.wd);
+    BARK_CHECK_ARG(smem <= 227 * 1024, "p_cap / n / d too large for the sweep kernel's shared memory");
+    BARK_CUDA(cudaFuncSetAttribute(sweep_trees_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    BARK_CUDA(cudaFuncSetAttribute(hyper_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(la::Smem)));
+    std::vector<cudaEvent_t> ev((size_t)n_sweeps * 3);
+    for (auto& e : ev) BARK_CUDA(cudaEventCreate(&e));
+    for (int64_t sidx = 0; sidx < n_sweeps; ++sidx) {
+        BARK_CUDA(cudaEventRecord(ev[sidx * 3 + 0], st));
+        sweep_trees_kernel<<<(unsigned)dims->chains, SW_THREADS, smem, st>>>(lay, workspace, forest, *params, sidx, n_sweeps,
+                                                                           seed, chain_offset, sweep_offset, nullptr, nullptr);
+        BARK_CUDA(cudaEventRecord(ev[sidx * 3 + 1], st));
+        hyper_kernel<<<(unsigned)dims->chains, la::THREADS, sizeof(la::Smem), st>>>(lay, workspace, *params, sidx, n_sweeps,
+                                                                                  seed, chain_offset, sweep_offset, nullptr, nullptr);
+        BARK_CUDA(cudaEventRecord(ev[sidx * 3 + 2], st));
+    }
+    BARK_LAUNCH_CHECK();
+    BARK_CUDA(cudaStreamSynchronize(st));
+    float tt = 0.f, th = 0.f;
+    for (int64_t sidx = 0; sidx < n_sweeps; ++sidx) {
+        float a = 0.f, b = 0.f;
+        BARK_CUDA(cudaEventElapsedTime(&a, ev[sidx * 3 + 0], ev[sidx * 3 + 1]));
+        BARK_CUDA(cudaEventElapsedTime(&b, ev[sidx * 3 + 1], ev[sidx * 3 + 2]));
+        tt += a; th += b;
+    }
+    for (auto& e : ev) cudaEventDestroy(e);
+    *ms_trees_host = tt;
+    *ms_hyper_host = th;
     return BARK_OK;
 }
 

@@ -19,7 +19,7 @@ namespace bark {
 struct ChainScalars {
     double noise, scale, sig, c;
     double q, ldt, mll, yy;
-    unsigned long long counters[8];
+    unsigned long long counters[16];
     int p_hi;           // used column extent (columns >= p_hi are free and identity-like)
     unsigned status;    // BARK_ST_* bits
     int pad0, pad1;

@@ -100,13 +100,22 @@ class ChainState:
                                              int(n_sweeps), C.c_uint64(seed & (2**64 - 1)), int(chain_offset),
                                              int(sweep_offset), _ptr(tape), _ptr(trace), _stream()))
 
+    def sweeps_timed(self, params: BARKTrainParams, n_sweeps: int, seed: int, chain_offset=0, sweep_offset=0):
+        """Measurement variant: returns (ms in the tree-sweep kernel, ms in the hyper kernel), summed over sweeps."""
+        cp = params.to_c()
+        a, b = C.c_float(0), C.c_float(0)
+        _lib.check(self.lib.bark_mcmc_sweeps_timed(C.byref(self.dims), _ptr(self.ws), self.dforest.soa(), C.byref(cp),
+                                                   int(n_sweeps), C.c_uint64(seed & (2**64 - 1)), int(chain_offset),
+                                                   int(sweep_offset), C.byref(a), C.byref(b), _stream()))
+        return a.value, b.value
+
     def read(self):
         """dict of per-chain device tensors: noise, scale, mll, status, counters (C,8), p_used."""
         torch = _lib.require_cuda()
         c, dev = self.chains, self.device
         out = dict(noise=torch.empty(c, dtype=torch.float64, device=dev), scale=torch.empty(c, dtype=torch.float64, device=dev),
                    mll=torch.empty(c, dtype=torch.float64, device=dev), status=torch.empty(c, dtype=torch.int32, device=dev),
-                   counters=torch.empty((c, 8), dtype=torch.int64, device=dev), p_used=torch.empty(c, dtype=torch.int32, device=dev))
+                   counters=torch.empty((c, 16), dtype=torch.int64, device=dev), p_used=torch.empty(c, dtype=torch.int32, device=dev))
         _lib.check(self.lib.bark_mcmc_read(C.byref(self.dims), _ptr(self.ws), _ptr(out["noise"]), _ptr(out["scale"]),
                                            _ptr(out["mll"]), _ptr(out["status"]), _ptr(out["counters"]), _ptr(out["p_used"]),
                                            _stream()))

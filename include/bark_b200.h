@@ -135,8 +135,17 @@ int bark_mcmc_sweeps(const bark_mcmc_dims* dims, void* workspace, bark_nodes_soa
                      int64_t n_sweeps, uint64_t seed, int64_t chain_offset, int64_t sweep_offset, const double* tape,
                      double* trace, void* stream);
 
-/* Read-out of per-chain scalars: each (chains) or NULL.  counters (chains, 8) u64:
- * [tree proposals issued, valid, accepted, hyper issued, hyper accepted, grow acc, prune acc, change acc]. */
+/* Measurement variant (bench only; SYNCHRONISES the stream): same work without tape/trace, with CUDA events
+ * recorded on `stream` around every kernel; returns the summed device time of the tree-sweep kernel and of the
+ * hyper-step kernel in milliseconds (host pointers). */
+int bark_mcmc_sweeps_timed(const bark_mcmc_dims* dims, void* workspace, bark_nodes_soa forest, const bark_params* params,
+                           int64_t n_sweeps, uint64_t seed, int64_t chain_offset, int64_t sweep_offset,
+                           float* ms_trees_host, float* ms_hyper_host, void* stream);
+
+/* Read-out of per-chain scalars: each (chains) or NULL.  counters (chains, 16) u64:
+ * [0 tree proposals issued, 1 valid, 2 accepted, 3 hyper issued, 4 hyper accepted, 5-7 grow/prune/change accepted,
+ *  8-10 grow/prune/change valid, 11 sum (extent/64)^2 over matvec evaluations, 12 same over accepted updates,
+ *  13 leaf-bitset columns scanned, 14-15 reserved]. */
 int bark_mcmc_read(const bark_mcmc_dims* dims, const void* workspace, double* noise, double* scale, double* mll,
                    uint32_t* status, uint64_t* counters, int32_t* p_used, void* stream);
 

@@ -335,3 +335,12 @@ def test_surrogate_fit_predict_end_to_end():
     assert np.allclose(mu_b, want_mu_b, rtol=1e-9, atol=1e-10) and np.allclose(sd_b, want_sd_b, rtol=1e-8, atol=1e-10)
     sur.fit(X, y_raw)  # warm start: continues from the last sample with warmup 0 (surrogates/bark.py:131-141)
     assert sur.bark_params.warmup_steps == 0 and sur.forest.shape == (2, 3, 10, 100)
+
+
+def test_synthetic_generator_matches_oracle():
+    from bark_b200 import synthetic
+    for kw in (dict(n=70, dim=5), dict(n=90, dim=6, cat_dim=4, num_cat=5, m_true=20, seed=3)):
+        a, b = synthetic.synthetic_problem(**kw), O.synthetic_problem(**kw)
+        for x, y in zip(a[:4], b[:4]):
+            assert np.array_equal(x, y)
+    assert synthetic.TreeFunction(m=7).forest.tobytes() == O.TreeFunction(m=7).forest.tobytes()
