@@ -12,6 +12,8 @@
 // n_u = u^T u, b' = b + (u^T y) d, and the proposal's log-MLL follows from ONE matvec  Binv v  (none for
 // prune, where Binv v = e_b - c Binv[:,b]) plus O(P) dot products (2x2 capacitance matrix).  On accept the
 // state takes a symmetric rank-2 update.  One CTA owns one chain for the whole sweep.
+#include <stdlib.h>
+
 #include <algorithm>
 #include <vector>
 
@@ -20,6 +22,7 @@
 #include "linalg.cuh"
 #include "mcmc_state.cuh"
 #include "proposal_device.cuh"
+#include "sweep_kernel.cuh"
 
 namespace bark {
 
@@ -212,354 +215,6 @@ chain_init_kernel(WsLayout lay, void* ws, bark_nodes_soa forest, const double* _
 }
 
 // =====================================================================================================
-// tree sweep: one CTA (1024 threads) per chain runs the m tree MH steps of one sweep
-// =====================================================================================================
-constexpr int SW_THREADS = 1024;
-
-struct SweepCtl {  // small shared control block
-    Prop prop;
-    double q, ldt, mll;
-    int p_hi;
-    int accept;
-};
-
-__host__ __device__ inline size_t sweep_smem_bytes(int L, int d, int P, int wd) {
-    size_t o = 0;
-    o += align256(sizeof(SweepCtl));
-    o += align256((size_t)L * 2);        // is_leaf, active
-    o += align256((size_t)L * 4 * 6);    // feat,left,right,parent,depth,thr
-    o += align256((size_t)d * 2 * 8);    // box
-    o += align256((size_t)d * 4);        // ft
-    o += align256((size_t)P * 8) * 3;    // vd, Wd, Wv
-    o += align256((size_t)wd * 4) * 2;   // upos, uneg
-    o += align256(64 * 8);               // red
-    return o;
-}
-
-__global__ void __launch_bounds__(SW_THREADS, 1)
-sweep_trees_kernel(WsLayout lay, void* ws, bark_nodes_soa forest, bark_params prm, int64_t sweep_in_call,
-                   int64_t n_sweeps_call, uint64_t seed, int64_t chain_offset, int64_t sweep_offset,
-                   const double* __restrict__ tape, double* __restrict__ trace) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int P = (int)lay.P, L = (int)lay.L, m = (int)lay.m, n = (int)lay.n, wd = (int)lay.wd, npad = (int)lay.npad;
-    const int d = (int)lay.d;
-    unsigned char* sp = smem_raw;
-    SweepCtl* ctl = (SweepCtl*)sp;           sp += align256(sizeof(SweepCtl));
-    TreeSmem T;
-    T.is_leaf = sp; T.active = sp + L;       sp += align256((size_t)L * 2);
-    T.feat = (uint32_t*)sp; T.left = T.feat + L; T.right = T.left + L; T.parent = T.right + L; T.depth = T.parent + L;
-    T.thr = (float*)(T.depth + L);           sp += align256((size_t)L * 4 * 6);
-    double* box = (double*)sp;               sp += align256((size_t)d * 2 * 8);
-    int32_t* ftc = (int32_t*)sp;             sp += align256((size_t)d * 4);
-    double* vd = (double*)sp;                sp += align256((size_t)P * 8);
-    double* Wd = (double*)sp;                sp += align256((size_t)P * 8);
-    double* Wv = (double*)sp;                sp += align256((size_t)P * 8);
-    uint32_t* upos = (uint32_t*)sp;          sp += align256((size_t)wd * 4);
-    uint32_t* uneg = (uint32_t*)sp;          sp += align256((size_t)wd * 4);
-    double* red = (double*)sp;
-
-    const int64_t chain = blockIdx.x;
-    ChainView cv = chain_view(lay, ws, chain);
-    SharedView sv = shared_view(lay, ws);
-    ChainScalars* sc = cv.sc;
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = SW_THREADS >> 5;
-
-    if (sc->status & (BARK_ST_COL_OVERFLOW | BARK_ST_TREE_OVERFLOW | BARK_ST_HYPER_MODE)) return;  // chain is dead
-
-    const double sig = sc->sig, c = sc->c, yy = sc->yy;
-    const double nlogsig = (double)n * log(sig);
-    if (tid == 0) {
-        ctl->q = sc->q; ctl->ldt = sc->ldt; ctl->mll = sc->mll; ctl->p_hi = sc->p_hi;
-    }
-    for (int e = tid; e < d; e += SW_THREADS) ftc[e] = sv.ft[e];
-    unsigned long long n_valid = 0, n_acc = 0, n_acc_move[3] = {0, 0, 0}, n_valid_move[3] = {0, 0, 0};  // thread 0 only
-    unsigned long long blk_eval = 0, blk_upd = 0, cols_scanned = 0;
-
-    const uint32_t g_chain = (uint32_t)(chain_offset + chain), g_sweep = (uint32_t)(sweep_offset + sweep_in_call);
-    const size_t tape_base = tape ? ((size_t)(chain * n_sweeps_call + sweep_in_call)) * (size_t)(m * TAPE_PER_TREE + TAPE_PER_HYPER) : 0;
-    double* trace_base = trace ? trace + ((size_t)(chain * n_sweeps_call + sweep_in_call)) * (size_t)(m + 1) * 3 : nullptr;
-
-    for (int t = 0; t < m; ++t) {
-        __syncthreads();
-        // ---- stage the tree and the root box
-        const int64_t g0 = (chain * (int64_t)m + t) * L;
-        for (int e = tid; e < L; e += SW_THREADS) {
-            T.is_leaf[e] = forest.is_leaf[g0 + e];
-            T.active[e] = forest.active[g0 + e];
-            T.feat[e] = forest.feature[g0 + e];
-            T.left[e] = forest.left[g0 + e];
-            T.right[e] = forest.right[g0 + e];
-            T.parent[e] = forest.parent[g0 + e];
-            T.depth[e] = forest.depth[g0 + e];
-            T.thr[e] = forest.threshold[g0 + e];
-        }
-        for (int e = tid; e < 2 * d; e += SW_THREADS) box[e] = sv.bounds[e];
-        __syncthreads();
-
-        // ---- proposal (warp 0)
-        double u[6];
-        if (wid == 0) {
-            if (tape) {
-                for (int k = 0; k < TAPE_PER_TREE; ++k) u[k] = tape[tape_base + (size_t)t * TAPE_PER_TREE + k];
-            } else {
-                rng_uniforms(seed, g_chain, g_sweep, (uint32_t)t, TAPE_PER_TREE, u);
-            }
-            Prop p = propose_tree_warp(T, L, box, ftc, d, cv.colmap + (size_t)t * L, cv.colused, P, prm, u, &sc->status);
-            if (lane == 0) ctl->prop = p;
-        }
-        __syncthreads();
-        const Prop p = ctl->prop;
-        const double cur_q = ctl->q, cur_ldt = ctl->ldt, cur_mll = ctl->mll;
-        const int p_hi = ctl->p_hi;
-
-        double new_q = cur_q, new_ldt = cur_ldt, new_mll = cur_mll;
-        double eta = 0.0, n_u = 0.0, M00 = 0.0, M01 = 0.0, M11 = 0.0, det = -1.0, Ur0 = 0.0, Ur1 = 0.0;
-        int pe64 = 0;
-        bool accept = false;
-
-        if (p.valid) {
-            const int a = p.a, b = p.b;
-            const int pe = max(p_hi, max(a, b) + 1);
-            pe64 = min(P, (pe + 63) & ~63);
-            // ---- phase 1: the moved-point masks u+ / u-, eta = u^T y, n_u = u^T u
-            double eta_part = 0.0;
-            int cnt_part = 0;
-            const uint32_t* bits_a = cv.bits + (size_t)a * wd;
-            const uint32_t* bits_b = cv.bits + (size_t)b * wd;
-            const double* xf = sv.Xt + (size_t)p.feat * npad;
-            const int ftype = ftc[p.feat];
-            for (int i = tid; i < npad; i += SW_THREADS) {
-                const int w = i >> 5;
-                bool pos = false, neg = false;
-                if (i < n) {
-                    const bool in_b = (bits_b[w] >> lane) & 1u;
-                    if (p.move == MOVE_GROW) {
-                        if (in_b) pos = !goes_left(xf[i], p.thr, ftype);
-                    } else if (p.move == MOVE_PRUNE) {
-                        pos = in_b;
-                    } else {  // change: b = left child's column, a = right child's column
-                        const bool in_a = (bits_a[w] >> lane) & 1u;
-                        if (in_a || in_b) {
-                            const bool gl = goes_left(xf[i], p.thr, ftype);
-                            pos = in_b && !gl;
-                            neg = in_a && gl;
-                        }
-                    }
-                    if (pos) { eta_part += sv.y[i]; ++cnt_part; }
-                    if (neg) { eta_part -= sv.y[i]; ++cnt_part; }
-                }
-                const unsigned bp = __ballot_sync(0xffffffffu, pos), bn = __ballot_sync(0xffffffffu, neg);
-                if (lane == 0) { upos[w] = bp; uneg[w] = bn; }
-            }
-            eta = block_sum(eta_part, red);
-            n_u = block_sum((double)cnt_part, red);  // exact (integers < 2^53)
-            // (block_sum ends with every thread past its barriers; upos/uneg are visible)
-
-            // ---- phase 2: v = Z^T u by AND + POPC over the leaf bitsets
-            for (int q = wid; q < pe64; q += nw) {
-                int cnt = 0;
-                if (q < pe) {
-                    const uint32_t* bq = cv.bits + (size_t)q * wd;
-                    for (int w = lane; w < wd; w += 32) {
-                        const uint32_t x = bq[w];
-                        cnt += __popc(x & upos[w]) - __popc(x & uneg[w]);
-                    }
-                }
-                cnt = warp_sum_int(cnt);
-                if (lane == 0) vd[q] = (double)cnt;
-            }
-            // ---- phase 3: Wd = Binv d (two rows), Wv = Binv v (matvec; closed form for prune)
-            const double* row_a = cv.Binv + (size_t)a * P;
-            const double* row_b = cv.Binv + (size_t)b * P;
-            for (int k = tid; k < pe64; k += SW_THREADS) Wd[k] = row_a[k] - row_b[k];
-            __syncthreads();
-            if (p.move == MOVE_PRUNE) {
-                for (int k = tid; k < pe64; k += SW_THREADS) Wv[k] = ((k == b) ? 1.0 : 0.0) - c * row_b[k];
-            } else {
-                for (int q = wid; q < pe64; q += nw) {
-                    const double* row = cv.Binv + (size_t)q * P;
-                    double acc0 = 0.0, acc1 = 0.0;
-#pragma unroll 4
-                    for (int k = lane * 2; k < pe64; k += 64) {
-                        const double2 x = *reinterpret_cast<const double2*>(row + k);
-                        const double2 vv = *reinterpret_cast<const double2*>(vd + k);
-                        acc0 = fma(x.x, vv.x, acc0);
-                        acc1 = fma(x.y, vv.y, acc1);
-                    }
-                    const double acc = warp_sum(acc0 + acc1);
-                    if (lane == 0) Wv[q] = acc;
-                }
-            }
-            __syncthreads();
-            // ---- phase 4: 2x2 capacitance matrix and the proposed log-MLL
-            double pvv = 0.0, pvw = 0.0;
-            for (int k = tid; k < pe64; k += SW_THREADS) {
-                pvv = fma(vd[k], Wv[k], pvv);
-                pvw = fma(vd[k], cv.w[k], pvw);
-            }
-            const double vWv = block_sum(pvv, red);
-            const double vw = block_sum(pvw, red);
-            const double dWd = Wd[a] - Wd[b];
-            const double dWv = Wv[a] - Wv[b];
-            const double dw = cv.w[a] - cv.w[b];
-            M00 = dWd;
-            M01 = 1.0 + dWv;
-            M11 = -n_u + vWv;
-            det = M00 * M11 - M01 * M01;                 // < 0 for an SPD B'
-            new_ldt = cur_ldt + log(-det);
-            const double bq = cur_q + 2.0 * eta * dw + eta * eta * dWd;  // b'^T Binv b'
-            Ur0 = dw + eta * dWd;                                         // d^T r,  r = Binv b'
-            Ur1 = vw + eta * dWv;                                         // v^T r
-            new_q = bq - (M11 * Ur0 * Ur0 - 2.0 * M01 * Ur0 * Ur1 + M00 * Ur1 * Ur1) / det;
-            new_mll = 0.5 * (-(yy - new_q) / sig - nlogsig - new_ldt);
-        }
-
-        // ---- MH accept (bark_sampler.py:257-264); every thread evaluates the same scalars
-        {
-            double u_acc;
-            if (tape) u_acc = tape[tape_base + (size_t)t * TAPE_PER_TREE + 4];
-            else {
-                double uu[6];
-                rng_uniforms(seed, g_chain, g_sweep, (uint32_t)t, TAPE_PER_TREE, uu);
-                u_acc = uu[4];
-            }
-            if (p.valid) {
-                const double log_alpha = p.lqp + (new_mll - cur_mll);
-                accept = log(u_acc) <= fmin(log_alpha, 0.0);
-            }
-            if (tid == 0) {
-                if (trace_base) {
-                    trace_base[t * 3 + 0] = p.valid ? p.lqp : -INFINITY;
-                    trace_base[t * 3 + 1] = new_mll;
-                    trace_base[t * 3 + 2] = accept ? 1.0 : 0.0;
-                }
-                if (p.valid) {
-                    ++n_valid;
-                    ++n_valid_move[p.move];
-                    const unsigned long long nb64 = (unsigned long long)(pe64 / 64);
-                    if (p.move != MOVE_PRUNE) blk_eval += nb64 * nb64;
-                    if (accept) blk_upd += nb64 * nb64;
-                    cols_scanned += (unsigned long long)pe64;
-                }
-            }
-        }
-
-        if (accept) {
-            __syncthreads();  // every thread has finished reading w / Binv for the evaluation
-            const int a = p.a, b = p.b;
-            // M^-1 = [[al, be],[be, ga]]
-            const double al = M11 / det, be = -M01 / det, ga = M00 / det;
-            const double cw_d = al * Ur0 + be * Ur1, cw_v = be * Ur0 + ga * Ur1;
-            // w' = (w + eta Wd) - Wd cw_d - Wv cw_v
-            for (int k = tid; k < pe64; k += SW_THREADS) cv.w[k] = cv.w[k] + eta * Wd[k] - Wd[k] * cw_d - Wv[k] * cw_v;
-            // Binv' = Binv - [Wd Wv] M^-1 [Wd Wv]^T   (symmetric rank-2, read-modify-write)
-            for (int q = wid; q < pe64; q += nw) {
-                double* row = cv.Binv + (size_t)q * P;
-                const double cq_d = al * Wd[q] + be * Wv[q], cq_v = be * Wd[q] + ga * Wv[q];
-#pragma unroll 4
-                for (int k = lane * 2; k < pe64; k += 64) {
-                    double2 x = *reinterpret_cast<double2*>(row + k);
-                    const double2 dd = *reinterpret_cast<const double2*>(Wd + k);
-                    const double2 vv = *reinterpret_cast<const double2*>(Wv + k);
-                    x.x -= cq_d * dd.x + cq_v * vv.x;
-                    x.y -= cq_d * dd.y + cq_v * vv.y;
-                    *reinterpret_cast<double2*>(row + k) = x;
-                }
-            }
-            // A' = A + v d^T + d v^T + n_u d d^T  (exact integers): columns, then rows, then the corner
-            for (int k = tid; k < pe64; k += SW_THREADS) {
-                const int vk = (int)vd[k];
-                cv.A[(size_t)k * P + a] += vk;
-                cv.A[(size_t)k * P + b] -= vk;
-            }
-            __syncthreads();
-            for (int k = tid; k < pe64; k += SW_THREADS) {
-                const int vk = (int)vd[k];
-                cv.A[(size_t)a * P + k] += vk;
-                cv.A[(size_t)b * P + k] -= vk;
-            }
-            // leaf bitsets
-            for (int w = tid; w < wd; w += SW_THREADS) {
-                const uint32_t ba = cv.bits[(size_t)a * wd + w], bb = cv.bits[(size_t)b * wd + w];
-                cv.bits[(size_t)a * wd + w] = (ba | upos[w]) & ~uneg[w];
-                cv.bits[(size_t)b * wd + w] = (bb & ~upos[w]) | uneg[w];
-            }
-            __syncthreads();
-            if (tid == 0) {
-                // corner term n_u d d^T
-                const int nuu = (int)n_u;
-                cv.A[(size_t)a * P + a] += nuu;
-                cv.A[(size_t)b * P + b] += nuu;
-                cv.A[(size_t)a * P + b] -= nuu;
-                cv.A[(size_t)b * P + a] -= nuu;
-                cv.b[a] += eta;
-                cv.b[b] -= eta;
-                // forest edit (tree_proposals.py:146-183) + column bookkeeping
-                uint16_t* cm = cv.colmap + (size_t)t * L;
-                if (p.move == MOVE_GROW) {
-                    const uint32_t dep = T.depth[p.node];
-                    for (int s2 = 0; s2 < 2; ++s2) {
-                        const int64_t g = g0 + (s2 ? p.sr : p.sl);
-                        forest.is_leaf[g] = 1; forest.feature[g] = 0; forest.threshold[g] = 0.f; forest.left[g] = 0;
-                        forest.right[g] = 0; forest.parent[g] = (uint32_t)p.node; forest.depth[g] = dep + 1;
-                        forest.active[g] = 1;
-                    }
-                    const int64_t g = g0 + p.node;
-                    forest.is_leaf[g] = 0; forest.feature[g] = (uint32_t)p.feat; forest.threshold[g] = p.thr;
-                    forest.left[g] = (uint32_t)p.sl; forest.right[g] = (uint32_t)p.sr; forest.active[g] = 1;
-                    cm[p.sl] = (uint16_t)b;   // left child keeps the old leaf's column
-                    cm[p.sr] = (uint16_t)a;   // right child takes the new column
-                    cm[p.node] = NO_COL;
-                    cv.colused[a >> 5] |= (1u << (a & 31));
-                    if (a + 1 > ctl->p_hi) ctl->p_hi = a + 1;
-                } else if (p.move == MOVE_PRUNE) {
-                    forest.active[g0 + p.sl] = 0;
-                    forest.active[g0 + p.sr] = 0;
-                    forest.is_leaf[g0 + p.node] = 1;
-                    cm[p.node] = (uint16_t)a;  // merged leaf keeps the left child's column
-                    cm[p.sl] = NO_COL;
-                    cm[p.sr] = NO_COL;
-                    cv.colused[b >> 5] &= ~(1u << (b & 31));
-                    cv.b[b] = 0.0;
-                } else {
-                    forest.feature[g0 + p.node] = (uint32_t)p.feat;
-                    forest.threshold[g0 + p.node] = p.thr;
-                }
-                ctl->q = new_q; ctl->ldt = new_ldt; ctl->mll = new_mll;
-                ++n_acc;
-                ++n_acc_move[p.move];
-            }
-            if (p.move == MOVE_PRUNE) {
-                // column b is now an empty leaf: make its row / column of Binv exactly (1/c) e_b
-                __syncthreads();
-                for (int k = tid; k < pe64; k += SW_THREADS) {
-                    const double v = (k == b) ? 1.0 / c : 0.0;
-                    cv.Binv[(size_t)b * P + k] = v;
-                    cv.Binv[(size_t)k * P + b] = v;
-                }
-                if (tid == 0) cv.w[b] = 0.0;
-            }
-        }
-    }
-    __syncthreads();
-    if (tid == 0) {
-        sc->q = ctl->q; sc->ldt = ctl->ldt; sc->mll = ctl->mll; sc->p_hi = ctl->p_hi;
-        sc->counters[0] += (unsigned long long)m;
-        sc->counters[1] += n_valid;
-        sc->counters[2] += n_acc;
-        sc->counters[5] += n_acc_move[0];
-        sc->counters[6] += n_acc_move[1];
-        sc->counters[7] += n_acc_move[2];
-        sc->counters[8] += n_valid_move[0];
-        sc->counters[9] += n_valid_move[1];
-        sc->counters[10] += n_valid_move[2];
-        sc->counters[11] += blk_eval;      // sum over matvec evaluations of (extent/64)^2
-        sc->counters[12] += blk_upd;       // sum over accepted updates of (extent/64)^2
-        sc->counters[13] += cols_scanned;  // leaf-bitset columns scanned for v = Z^T u
-    }
-}
-
-// =====================================================================================================
 // hyper step: noise/scale MH with a full re-evaluation (bark_sampler.py:266-282).  One CTA per chain.
 // =====================================================================================================
 __global__ void __launch_bounds__(la::THREADS, 1)
@@ -688,6 +343,40 @@ static int check_dims(const bark_mcmc_dims* dm) {
     return 1;
 }
 
+// Cluster size for the tree sweep: the largest R in {1,2,4} with chains*R CTAs resident at once (1 CTA / SM).
+static int pick_cluster_size(int64_t chains) {
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const char* env = getenv("BARK_SWEEP_CLUSTER");
+    if (env) {
+        const int r = atoi(env);
+        if (r == 1 || r == 2 || r == 4) return r;
+    }
+    int R = 1;
+    while (R < SW_MAX_R && chains * (R * 2) <= sms) R *= 2;
+    return R;
+}
+
+static cudaError_t launch_sweep_trees(int R, size_t smem, cudaStream_t st, const WsLayout& lay, void* ws,
+                                      bark_nodes_soa forest, const bark_params& prm, int64_t sidx, int64_t n_sweeps,
+                                      uint64_t seed, int64_t chain_offset, int64_t sweep_offset, const double* tape,
+                                      double* trace) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(lay.chains * R));
+    cfg.blockDim = dim3(SW_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)R;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, sweep_trees_kernel, lay, ws, forest, prm, sidx, n_sweeps, seed, chain_offset,
+                              sweep_offset, tape, trace);
+}
+
 }  // namespace bark
 
 using namespace bark;
@@ -728,9 +417,10 @@ int bark_mcmc_sweeps(const bark_mcmc_dims* dims, void* workspace, bark_nodes_soa
     BARK_CHECK_ARG(smem <= 227 * 1024, "p_cap / n / d too large for the sweep kernel's shared memory");
     BARK_CUDA(cudaFuncSetAttribute(sweep_trees_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     BARK_CUDA(cudaFuncSetAttribute(hyper_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(la::Smem)));
+    const int R = pick_cluster_size(dims->chains);
     for (int64_t sidx = 0; sidx < n_sweeps; ++sidx) {
-        sweep_trees_kernel<<<(unsigned)dims->chains, SW_THREADS, smem, st>>>(lay, workspace, forest, *params, sidx, n_sweeps,
-                                                                           seed, chain_offset, sweep_offset, tape, trace);
+        BARK_CUDA(launch_sweep_trees(R, smem, st, lay, workspace, forest, *params, sidx, n_sweeps, seed, chain_offset,
+                                     sweep_offset, tape, trace));
         hyper_kernel<<<(unsigned)dims->chains, la::THREADS, sizeof(la::Smem), st>>>(lay, workspace, *params, sidx, n_sweeps,
                                                                                   seed, chain_offset, sweep_offset, tape, trace);
     }
@@ -750,12 +440,13 @@ int bark_mcmc_sweeps_timed(const bark_mcmc_dims* dims, void* workspace, bark_nod
     BARK_CHECK_ARG(smem <= 227 * 1024, "p_cap / n / d too large for the sweep kernel's shared memory");
     BARK_CUDA(cudaFuncSetAttribute(sweep_trees_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     BARK_CUDA(cudaFuncSetAttribute(hyper_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(la::Smem)));
+    const int R = pick_cluster_size(dims->chains);
     std::vector<cudaEvent_t> ev((size_t)n_sweeps * 3);
     for (auto& e : ev) BARK_CUDA(cudaEventCreate(&e));
     for (int64_t sidx = 0; sidx < n_sweeps; ++sidx) {
         BARK_CUDA(cudaEventRecord(ev[sidx * 3 + 0], st));
-        sweep_trees_kernel<<<(unsigned)dims->chains, SW_THREADS, smem, st>>>(lay, workspace, forest, *params, sidx, n_sweeps,
-                                                                           seed, chain_offset, sweep_offset, nullptr, nullptr);
+        BARK_CUDA(launch_sweep_trees(R, smem, st, lay, workspace, forest, *params, sidx, n_sweeps, seed, chain_offset,
+                                     sweep_offset, nullptr, nullptr));
         BARK_CUDA(cudaEventRecord(ev[sidx * 3 + 1], st));
         hyper_kernel<<<(unsigned)dims->chains, la::THREADS, sizeof(la::Smem), st>>>(lay, workspace, *params, sidx, n_sweeps,
                                                                                   seed, chain_offset, sweep_offset, nullptr, nullptr);

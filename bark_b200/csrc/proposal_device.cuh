@@ -229,7 +229,7 @@ __device__ __forceinline__ Prop propose_tree_warp(const TreeSmem& T, int L, doub
         // free leaf column for the right child (lowest index first)
         int fcol = -1;
         for (int w = 0; w < P / 32 && fcol < 0; ++w) {
-            const uint32_t fr = ~colused[w];
+            const uint32_t fr = ~__ldcg(colused + w);
             if (fr) fcol = w * 32 + __ffs(fr) - 1;
         }
         if (fcol < 0) {
@@ -245,11 +245,11 @@ __device__ __forceinline__ Prop propose_tree_warp(const TreeSmem& T, int L, doub
         const double log_q = __dsub_rn(log((double)nT), log((double)w1));
         p.lqp = __dadd_rn(log_q, log_prior_ratio_at_depth(depth, prm.alpha, prm.beta));
         p.sl = s0; p.sr = s1;
-        p.a = fcol; p.b = (int)cm[node];
+        p.a = fcol; p.b = (int)__ldcg(cm + node);
     } else {
         p.sl = (int)T.left[node];
         p.sr = (int)T.right[node];
-        const int pL = (int)cm[p.sl], pR = (int)cm[p.sr];
+        const int pL = (int)__ldcg(cm + p.sl), pR = (int)__ldcg(cm + p.sr);
         if (move == MOVE_PRUNE) {
             const double log_q = __dsub_rn(log((double)nS), log((double)(nT - 1)));  // :111-114
             p.lqp = __dadd_rn(log_q, -log_prior_ratio_at_depth(depth, prm.alpha, prm.beta));
