@@ -33,7 +33,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
         raise RuntimeError("nvcc not found: cannot build libbark_b200.so")
-    cmd = [nvcc, *NVCC_FLAGS, "-o", LIB_PATH + ".tmp", *[os.path.join(CSRC, s) for s in SOURCES]]
+    extra = os.environ.get("BARK_NVCC_EXTRA", "").split()  # e.g. -DBARK_PHASE_TIMING for the instrumented build
+    cmd = [nvcc, *NVCC_FLAGS, *extra, "-o", LIB_PATH + ".tmp", *[os.path.join(CSRC, s) for s in SOURCES]]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     res = subprocess.run(cmd, capture_output=True, text=True)

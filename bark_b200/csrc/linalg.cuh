@@ -13,6 +13,8 @@
 // Replaces np.linalg.inv / np.linalg.slogdet of src/bark/fitting/bark_sampler.py:160-161,269-270 and
 // src/bark/tree_kernels/tree_gps.py:102.
 #pragma once
+#include <cooperative_groups.h>
+
 #include "common.cuh"
 
 namespace bark {
@@ -55,8 +57,8 @@ __device__ __forceinline__ void gemm_nt_tile(double* C, int64_t ldc, const doubl
             const int r = e >> 5, k = e & 31;
             double va = 0.0, vb = 0.0;
             if (k0 + k < K) {
-                if (r < mr) va = A[(int64_t)r * lda + k0 + k];
-                if (r < nc) vb = B[(int64_t)r * ldb + k0 + k];
+                if (r < mr) va = __ldcg(A + (int64_t)r * lda + k0 + k);
+                if (r < nc) vb = __ldcg(B + (int64_t)r * ldb + k0 + k);
             }
             s.As[r][k] = va;
             s.Bs[r][k] = vb;
@@ -85,9 +87,9 @@ __device__ __forceinline__ void gemm_nt_tile(double* C, int64_t ldc, const doubl
                 if (c < nc && (!lower_only || c <= r)) {
                     double* p = C + (int64_t)r * ldc + c;
                     if (MODE == ACC_SUB)
-                        *p -= acc[i][j];
+                        __stcg(p, __ldcg(p) - acc[i][j]);
                     else
-                        *p = acc[i][j];
+                        __stcg(p, acc[i][j]);
                 }
             }
         }
@@ -100,7 +102,7 @@ __device__ __forceinline__ void load_pivot_block(const double* G, int64_t ld, in
         const int r = e / NB, c = e % NB;
         double v;
         if (r < bs && c < bs)
-            v = (c <= r) ? G[(int64_t)r * ld + c] : G[(int64_t)c * ld + r];
+            v = (c <= r) ? __ldcg(G + (int64_t)r * ld + c) : __ldcg(G + (int64_t)c * ld + r);
         else
             v = (r == c) ? 1.0 : 0.0;
         s.D[r][c] = v;
@@ -142,125 +144,152 @@ __device__ __forceinline__ bool sweep_pivot_block(Smem& s) {
     return ok;
 }
 
+// A "team" is the set of CTAs that cooperate on one matrix: a single CTA (SoloTeam) or a thread-block cluster
+// (ClusterTeam, used for the exact refresh of B^-1).  Data handed between CTAs goes through global memory with
+// .cg accesses and a team barrier (cluster barrier = release/acquire at cluster scope).
+struct SoloTeam {
+    __device__ __forceinline__ int rank() const { return 0; }
+    __device__ __forceinline__ int size() const { return 1; }
+    __device__ __forceinline__ void sync() const { __syncthreads(); }
+};
+struct ClusterTeam {
+    cooperative_groups::cluster_group c;
+    __device__ __forceinline__ int rank() const { return (int)c.block_rank(); }
+    __device__ __forceinline__ int size() const { return (int)c.num_blocks(); }
+    __device__ __forceinline__ void sync() const { c.sync(); }
+};
+
 // Blocked symmetric sweep of the n x n SPD matrix W (lower triangle valid on entry, leading dim ld).
-//   CK, GK : scratch panels, n x NB doubles each (row-major, ld = NB).
+//   CK, GK : scratch panels, n x NB doubles each (row-major, ld = NB);  DG : NB x NB scratch (pivot inverse).
 //   yv     : optional (FULL == false) mutable copy of a right-hand side; on exit *quad = y^T W^-1 y.
-// Returns log|W| to every thread.  *status |= BARK_ST_NOT_SPD on a non-positive pivot.
-template <bool FULL>
-__device__ double block_sweep(double* W, int64_t ld, int n, double* CK, double* GK, double* yv, double* quad,
-                              Smem& s, uint32_t* status) {
+// Returns log|W| (valid on team rank 0, every thread).  *status |= BARK_ST_NOT_SPD on a non-positive pivot.
+template <bool FULL, class Team>
+__device__ double block_sweep(double* W, int64_t ld, int n, double* CK, double* GK, double* DG, double* yv,
+                              double* quad, Smem& s, uint32_t* status, const Team& team) {
     const int tid = threadIdx.x;
     const int nblk = (n + NB - 1) / NB;
+    const int trank = team.rank(), tsize = team.size();
     double logdet = 0.0, q = 0.0;
     for (int kb = 0; kb < nblk; ++kb) {
         const int k0 = kb * NB;
         const int bs = min(NB, n - k0);
-        load_pivot_block(W + (int64_t)k0 * ld + k0, ld, bs, s);
-        const bool ok = sweep_pivot_block(s);  // s.D = -Dinv
-        if (!ok && tid == 0 && status) atomicOr(status, BARK_ST_NOT_SPD);
-        // log det of the pivot block
-        {
-            double lg = (tid < NB) ? log(s.piv[tid]) : 0.0;
-            logdet += block_sum(lg, s.red);
-        }
-        // right-hand side elimination (forward mode): t = Dinv y_k ; quad += y_k^T t
-        if (!FULL && yv) {
-            if (tid < NB) {
-                double t = 0.0;
-                if (tid < bs)
-                    for (int c = 0; c < bs; ++c) t -= s.D[tid][c] * yv[k0 + c];
-                s.tv[tid] = t;
-            }
-            __syncthreads();
-            double part = (tid < bs) ? s.tv[tid] * yv[k0 + tid] : 0.0;
-            q += block_sum(part, s.red);
-        }
         const int rlo = FULL ? 0 : k0 + bs;  // first row taking part in the update
+        // ---- P0 (rank 0): invert the pivot block in shared memory, publish Dinv, eliminate the right-hand side
+        if (trank == 0) {
+            load_pivot_block(W + (int64_t)k0 * ld + k0, ld, bs, s);
+            const bool ok = sweep_pivot_block(s);  // s.D = -Dinv
+            if (!ok && tid == 0 && status) atomicOr(status, BARK_ST_NOT_SPD);
+            {
+                double lg = (tid < NB) ? log(s.piv[tid]) : 0.0;
+                logdet += block_sum(lg, s.red);
+            }
+            for (int e = tid; e < NB * NB; e += THREADS) __stcg(DG + e, -s.D[e / NB][e % NB]);
+            if (!FULL && yv) {
+                if (tid < NB) {
+                    double t = 0.0;
+                    if (tid < bs)
+                        for (int c = 0; c < bs; ++c) t -= s.D[tid][c] * yv[k0 + c];
+                    s.tv[tid] = t;
+                }
+                __syncthreads();
+                double part = (tid < bs) ? s.tv[tid] * yv[k0 + tid] : 0.0;
+                q += block_sum(part, s.red);
+            }
+        }
         if (rlo >= n && !FULL) break;
-        // gather the pivot block column: CK[i][c] = W[i][k0+c] (i below) or W[k0+c][i] (i above); 0 inside block
-        for (int64_t e = tid; e < (int64_t)(n - rlo) * NB; e += THREADS) {
-            const int i = rlo + (int)(e / NB), c = (int)(e % NB);
-            double v = 0.0;
-            if (c < bs) {
-                if (i >= k0 + bs)
-                    v = W[(int64_t)i * ld + k0 + c];
-                else if (i < k0)
-                    v = W[(int64_t)(k0 + c) * ld + i];
+        team.sync();
+        // ---- P1: pivot column panel CK (gathered) and GK = CK * Dinv, by 128-row tiles round-robin over the team
+        {
+            int rt = 0;
+            for (int ti = rlo; ti < n; ti += TILE, ++rt) {
+                if (rt % tsize != trank) continue;
+                const int mr = min(TILE, n - ti);
+                for (int e = tid; e < mr * NB; e += THREADS) {
+                    const int i = ti + e / NB, c = e % NB;
+                    double v = 0.0;
+                    if (c < bs) {
+                        if (i >= k0 + bs)
+                            v = __ldcg(W + (int64_t)i * ld + k0 + c);
+                        else if (i < k0)
+                            v = __ldcg(W + (int64_t)(k0 + c) * ld + i);
+                    }
+                    __stcg(CK + (int64_t)i * NB + c, v);
+                }
+                __syncthreads();
+                gemm_nt_tile<ACC_SET>(GK + (int64_t)ti * NB, NB, CK + (int64_t)ti * NB, NB, DG, NB, mr, NB, bs, false, s);
+                if (!FULL && yv && trank == 0) {
+                    // y_r -= G_r . y_k = C_r . t   (forward mode runs on a solo team)
+                    for (int i = ti + tid; i < ti + mr; i += THREADS) {
+                        const double* ck = CK + (int64_t)i * NB;
+                        double a = 0.0;
+                        for (int c = 0; c < bs; ++c) a += __ldcg(ck + c) * s.tv[c];
+                        yv[i] -= a;
+                    }
+                }
             }
-            CK[(int64_t)i * NB + c] = v;
         }
-        // Dinv into global scratch? -- no: GK = CK * Dinv computed straight from shared memory (Dinv = -s.D).
-        __syncthreads();
-        for (int64_t e = tid; e < (int64_t)(n - rlo) * NB; e += THREADS) {
-            const int i = rlo + (int)(e / NB), c = (int)(e % NB);
-            const double* ck = CK + (int64_t)i * NB;
-            double g = 0.0;
-#pragma unroll 8
-            for (int k = 0; k < NB; ++k) g -= ck[k] * s.D[k][c];
-            GK[(int64_t)i * NB + c] = g;
-        }
-        // forward mode: y_r -= G_r . y_k = C_r . t
-        if (!FULL && yv) {
-            for (int i = rlo + tid; i < n; i += THREADS) {
-                const double* ck = CK + (int64_t)i * NB;
-                double a = 0.0;
-                for (int c = 0; c < bs; ++c) a += ck[c] * s.tv[c];
-                yv[i] -= a;
-            }
-        }
-        __syncthreads();
-        // trailing update on the lower triangle: W_ij -= G_i C_j^T
-        for (int ti = rlo; ti < n; ti += TILE) {
-            const int mr = min(TILE, n - ti);
-            for (int tj = rlo; tj <= ti; tj += TILE) {
-                const int nc = min(TILE, n - tj);
-                gemm_nt_tile<ACC_SUB>(W + (int64_t)ti * ld + tj, ld, GK + (int64_t)ti * NB, NB, CK + (int64_t)tj * NB,
-                                      NB, mr, nc, bs, ti == tj, s);
+        team.sync();
+        // ---- P2: trailing update on the lower triangle, W_ij -= G_i C_j^T, tiles round-robin over the team
+        {
+            int idx = 0;
+            for (int ti = rlo; ti < n; ti += TILE) {
+                const int mr = min(TILE, n - ti);
+                for (int tj = rlo; tj <= ti; tj += TILE, ++idx) {
+                    if (idx % tsize != trank) continue;
+                    const int nc = min(TILE, n - tj);
+                    gemm_nt_tile<ACC_SUB>(W + (int64_t)ti * ld + tj, ld, GK + (int64_t)ti * NB, NB,
+                                          CK + (int64_t)tj * NB, NB, mr, nc, bs, ti == tj, s);
+                }
             }
         }
         if (FULL) {
-            __syncthreads();
-            // write the swept pivot column/row back: W_ik = G_i (i below), W_kj = G_j^T (j above), W_kk = -Dinv
-            for (int64_t e = tid; e < (int64_t)n * NB; e += THREADS) {
-                const int i = (int)(e / NB), c = (int)(e % NB);
-                if (c >= bs) continue;
-                if (i >= k0 + bs)
-                    W[(int64_t)i * ld + k0 + c] = GK[(int64_t)i * NB + c];
-                else if (i < k0)
-                    W[(int64_t)(k0 + c) * ld + i] = GK[(int64_t)i * NB + c];
-                else if (c <= i - k0)
-                    W[(int64_t)i * ld + k0 + c] = s.D[i - k0][c];
+            team.sync();
+            // ---- P3: write the swept pivot column/row back: W_ik = G_i (below), W_kj = G_j^T (above), W_kk = -Dinv
+            int rt = 0;
+            for (int ti = 0; ti < n; ti += TILE, ++rt) {
+                if (rt % tsize != trank) continue;
+                const int mr = min(TILE, n - ti);
+                for (int e = tid; e < mr * NB; e += THREADS) {
+                    const int i = ti + e / NB, c = e % NB;
+                    if (c >= bs) continue;
+                    if (i >= k0 + bs)
+                        __stcg(W + (int64_t)i * ld + k0 + c, __ldcg(GK + (int64_t)i * NB + c));
+                    else if (i < k0)
+                        __stcg(W + (int64_t)(k0 + c) * ld + i, __ldcg(GK + (int64_t)i * NB + c));
+                    else if (c <= i - k0)
+                        __stcg(W + (int64_t)i * ld + k0 + c, -__ldcg(DG + (i - k0) * NB + c));
+                }
             }
         }
-        __syncthreads();
+        team.sync();
     }
     if (FULL) {
         // W currently holds -W^-1 on the lower triangle: negate and mirror (32x32 tiles through shared memory).
-        __syncthreads();
         double(*T)[33] = reinterpret_cast<double(*)[33]>(&s.As[0][0]);  // 32 x 33 tile
         const int tx = tid & 31, ty = tid >> 5;                            // 32 x 16
         const int nt = (n + 31) / 32;
+        int idx = 0;
         for (int bi = 0; bi < nt; ++bi) {
-            for (int bj = 0; bj <= bi; ++bj) {
+            for (int bj = 0; bj <= bi; ++bj, ++idx) {
+                if (idx % tsize != trank) continue;
                 __syncthreads();
                 for (int r = ty; r < 32; r += 16) {
                     const int gi = bi * 32 + r, gj = bj * 32 + tx;
                     double v = 0.0;
                     if (gi < n && gj < n && gj <= gi) {
-                        v = -W[(int64_t)gi * ld + gj];
-                        W[(int64_t)gi * ld + gj] = v;
+                        v = -__ldcg(W + (int64_t)gi * ld + gj);
+                        __stcg(W + (int64_t)gi * ld + gj, v);
                     }
                     T[r][tx] = v;
                 }
                 __syncthreads();
                 for (int r = ty; r < 32; r += 16) {
-                    // element (gj2, gi2) of the upper triangle = T[tx][r] transposed
                     const int gi = bj * 32 + r, gj = bi * 32 + tx;  // row in block bj, column in block bi
-                    if (gi < n && gj < n && gj > gi) W[(int64_t)gi * ld + gj] = T[tx][r];
+                    if (gi < n && gj < n && gj > gi) __stcg(W + (int64_t)gi * ld + gj, T[tx][r]);
                 }
             }
         }
-        __syncthreads();
+        team.sync();
     }
     if (quad) *quad = q;
     return logdet;

@@ -196,7 +196,7 @@ chain_init_kernel(WsLayout lay, void* ws, bark_nodes_soa forest, const double* _
     unsigned* stp = &cv.sc->status;
     if (tid == 0) *stp = 0;
     __syncthreads();
-    const double logdet = la::block_sweep<true>(cv.Binv, P, ptot, cv.CK, cv.GK, nullptr, nullptr, s, stp);
+    const double logdet = la::block_sweep<true>(cv.Binv, P, ptot, cv.CK, cv.GK, cv.DG, nullptr, nullptr, s, stp, la::SoloTeam());
     const double q = matvec_w_q(cv.Binv, P, ptot, cv.b, cv.w, s.red);
     const double ldt = logdet - (double)ptot * log(c);
     if (tid == 0) {
@@ -210,16 +210,24 @@ chain_init_kernel(WsLayout lay, void* ws, bark_nodes_soa forest, const double* _
         sc->yy = yy;
         sc->mll = mll_from(yy, q, sig, (double)n, ldt);
         for (int k = 0; k < 16; ++k) sc->counters[k] = 0ull;
+        for (int k = 0; k < 12; ++k) sc->phase_cycles[k] = 0ull;
         sc->p_hi = ptot;
+        sc->hyper_accept = 0;
     }
 }
 
 // =====================================================================================================
-// hyper step: noise/scale MH with a full re-evaluation (bark_sampler.py:266-282).  One CTA per chain.
+// hyper step: noise/scale MH with a full re-evaluation (bark_sampler.py:266-282).
+//   hyper_eval_kernel    one CTA per chain: proposal, B' = c'I + A, forward block sweep -> MLL', MH decision
+//   hyper_refresh_kernel one 8-CTA cluster per chain, only for accepted chains: exact B'^-1 (full block sweep
+//                        with tiles spread over the cluster), w = B'^-1 b, q, ldt, mll  (the reference
+//                        refreshes K^-1 at the same point, :276-282)
 // =====================================================================================================
+constexpr int HYPER_CLUSTER = 8;
+
 __global__ void __launch_bounds__(la::THREADS, 1)
-hyper_kernel(WsLayout lay, void* ws, bark_params prm, int64_t sweep_in_call, int64_t n_sweeps_call, uint64_t seed,
-             int64_t chain_offset, int64_t sweep_offset, const double* __restrict__ tape, double* __restrict__ trace) {
+hyper_eval_kernel(WsLayout lay, void* ws, bark_params prm, int64_t sweep_in_call, int64_t n_sweeps_call, uint64_t seed,
+                  int64_t chain_offset, int64_t sweep_offset, const double* __restrict__ tape, double* __restrict__ trace) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     la::Smem& s = *reinterpret_cast<la::Smem*>(smem_raw);
     __shared__ HyperProp hp;
@@ -252,6 +260,7 @@ hyper_kernel(WsLayout lay, void* ws, bark_params prm, int64_t sweep_in_call, int
         for (int w = P / 32 - 1; w >= 0; --w)
             if (cv.colused[w]) { hi = w * 32 + 32 - __clz(cv.colused[w]); break; }
         s_phi = hi;
+        sc->hyper_accept = 0;
         if (hp.status) atomicOr(&sc->status, hp.status);
     }
     __syncthreads();
@@ -265,7 +274,8 @@ hyper_kernel(WsLayout lay, void* ws, bark_params prm, int64_t sweep_in_call, int
     for (int k = tid; k < ph; k += la::THREADS) cv.yv[k] = cv.b[k];
     __syncthreads();
     double quad = 0.0;
-    const double logdet = la::block_sweep<false>(cv.Wk, P, ph, cv.CK, cv.GK, cv.yv, &quad, s, &sc->status);
+    const double logdet = la::block_sweep<false>(cv.Wk, P, ph, cv.CK, cv.GK, cv.DG, cv.yv, &quad, s, &sc->status,
+                                                 la::SoloTeam());
     const double ldt2 = logdet - (double)ph * log(c2);
     const double mll2 = mll_from(yy, quad, sig2, (double)n, ldt2);
     const double log_alpha = hp.lqp + (mll2 - cur_mll);
@@ -277,22 +287,59 @@ hyper_kernel(WsLayout lay, void* ws, bark_params prm, int64_t sweep_in_call, int
         }
         sc->counters[3] += 1ull;
         sc->p_hi = ph;
+        if (accept) {
+            sc->prop_noise = hp.noise;
+            sc->prop_scale = hp.scale;
+            sc->hyper_accept = 1;
+            sc->counters[4] += 1ull;
+        }
     }
-    if (!accept) return;
+}
 
-    // accepted: exact refresh of the running state (the reference refreshes K^-1 here too, :276-282)
-    fill_B_lower(cv.Binv, cv.A, P, ph, c2);
-    __syncthreads();
-    const double logdet_f = la::block_sweep<true>(cv.Binv, P, ph, cv.CK, cv.GK, nullptr, nullptr, s, &sc->status);
-    for (int k = ph + tid; k < P; k += la::THREADS) cv.Binv[(size_t)k * P + k] = 1.0 / c2;
-    __syncthreads();
-    const double q = matvec_w_q(cv.Binv, P, ph, cv.b, cv.w, s.red);
-    if (tid == 0) {
-        const double ldt = logdet_f - (double)ph * log(c2);
-        sc->noise = hp.noise; sc->scale = hp.scale; sc->sig = sig2; sc->c = c2;
-        sc->q = q; sc->ldt = ldt;
-        sc->mll = mll_from(yy, q, sig2, (double)n, ldt);
-        sc->counters[4] += 1ull;
+__global__ void __launch_bounds__(la::THREADS, 1)
+hyper_refresh_kernel(WsLayout lay, void* ws) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    la::Smem& s = *reinterpret_cast<la::Smem*>(smem_raw);
+    la::ClusterTeam team{cooperative_groups::this_cluster()};
+    const int trank = team.rank(), tsize = team.size();
+    const int64_t chain = blockIdx.x / tsize;
+    ChainView cv = chain_view(lay, ws, chain);
+    ChainScalars* sc = cv.sc;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = la::THREADS >> 5;
+    const int P = (int)lay.P, m = (int)lay.m, n = (int)lay.n;
+    if (__ldcg(&sc->hyper_accept) == 0) return;  // uniform over the cluster (written by the previous kernel)
+    const int ph = sc->p_hi;
+    const double noise = sc->prop_noise, scale = sc->prop_scale;
+    const double sig2 = noise + 1e-6;
+    const double c2 = sig2 * (double)m / scale;
+
+    // B' lower triangle, rows split over the cluster
+    for (int r = trank; r < ph; r += tsize)
+        for (int k = tid; k <= r; k += la::THREADS)
+            __stcg(cv.Binv + (size_t)r * P + k, (double)__ldcg(cv.A + (size_t)r * P + k) + (r == k ? c2 : 0.0));
+    team.sync();
+    const double logdet_f = la::block_sweep<true>(cv.Binv, P, ph, cv.CK, cv.GK, cv.DG, nullptr, nullptr, s, &sc->status, team);
+    for (int k = ph + trank * la::THREADS + tid; k < P; k += tsize * la::THREADS) __stcg(cv.Binv + (size_t)k * P + k, 1.0 / c2);
+    // w = Binv b, rows split over the cluster
+    for (int r = trank * nw + wid; r < ph; r += tsize * nw) {
+        const double* row = cv.Binv + (size_t)r * P;
+        double acc = 0.0;
+        for (int k = lane; k < ph; k += 32) acc = fma(__ldcg(row + k), cv.b[k], acc);
+        acc = warp_sum(acc);
+        if (lane == 0) __stcg(cv.w + r, acc);
+    }
+    team.sync();
+    if (trank == 0) {
+        double part = 0.0;
+        for (int k = tid; k < ph; k += la::THREADS) part = fma(cv.b[k], __ldcg(cv.w + k), part);
+        const double q = block_sum(part, s.red);
+        if (tid == 0) {
+            const double ldt = logdet_f - (double)ph * log(c2);
+            sc->noise = noise; sc->scale = scale; sc->sig = sig2; sc->c = c2;
+            sc->q = q; sc->ldt = ldt;
+            sc->mll = mll_from(sc->yy, q, sig2, (double)n, ldt);
+            sc->hyper_accept = 0;
+        }
     }
 }
 
@@ -310,6 +357,13 @@ __global__ void mcmc_read_kernel(WsLayout lay, const void* ws, double* noise, do
     if (mll) mll[c] = sc->mll;
     if (status) status[c] = sc->status;
     if (counters) for (int k = 0; k < 16; ++k) counters[c * 16 + k] = sc->counters[k];
+#ifdef BARK_PHASE_TIMING
+    if (counters && c == 0) {  // debug build: chain 0's phase totals overwrite the counters of the LAST chain slot
+        printf("phase_cycles chain0:");
+        for (int k = 0; k < 12; ++k) printf(" %llu", sc->phase_cycles[k]);
+        printf("\n");
+    }
+#endif
     if (p_used) {
         int cnt = 0;
         for (int w = 0; w < lay.P / 32; ++w) cnt += __popc(cv.colused[w]);
@@ -355,6 +409,26 @@ static int pick_cluster_size(int64_t chains) {
     int R = 1;
     while (R < SW_MAX_R && chains * (R * 2) <= sms) R *= 2;
     return R;
+}
+
+static cudaError_t launch_hyper(cudaStream_t st, const WsLayout& lay, void* ws, const bark_params& prm, int64_t sidx,
+                                int64_t n_sweeps, uint64_t seed, int64_t chain_offset, int64_t sweep_offset,
+                                const double* tape, double* trace) {
+    hyper_eval_kernel<<<(unsigned)lay.chains, la::THREADS, sizeof(la::Smem), st>>>(lay, ws, prm, sidx, n_sweeps, seed,
+                                                                               chain_offset, sweep_offset, tape, trace);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(lay.chains * HYPER_CLUSTER));
+    cfg.blockDim = dim3(la::THREADS);
+    cfg.dynamicSmemBytes = sizeof(la::Smem);
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = HYPER_CLUSTER;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, hyper_refresh_kernel, lay, ws);
 }
 
 static cudaError_t launch_sweep_trees(int R, size_t smem, cudaStream_t st, const WsLayout& lay, void* ws,
@@ -416,13 +490,13 @@ int bark_mcmc_sweeps(const bark_mcmc_dims* dims, void* workspace, bark_nodes_soa
     const size_t smem = sweep_smem_bytes((int)lay.L, (int)lay.d, (int)lay.P, (int)lay.wd);
     BARK_CHECK_ARG(smem <= 227 * 1024, "p_cap / n / d too large for the sweep kernel's shared memory");
     BARK_CUDA(cudaFuncSetAttribute(sweep_trees_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    BARK_CUDA(cudaFuncSetAttribute(hyper_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(la::Smem)));
+    BARK_CUDA(cudaFuncSetAttribute(hyper_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(la::Smem)));
+    BARK_CUDA(cudaFuncSetAttribute(hyper_refresh_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(la::Smem)));
     const int R = pick_cluster_size(dims->chains);
     for (int64_t sidx = 0; sidx < n_sweeps; ++sidx) {
         BARK_CUDA(launch_sweep_trees(R, smem, st, lay, workspace, forest, *params, sidx, n_sweeps, seed, chain_offset,
                                      sweep_offset, tape, trace));
-        hyper_kernel<<<(unsigned)dims->chains, la::THREADS, sizeof(la::Smem), st>>>(lay, workspace, *params, sidx, n_sweeps,
-                                                                                  seed, chain_offset, sweep_offset, tape, trace);
+        BARK_CUDA(launch_hyper(st, lay, workspace, *params, sidx, n_sweeps, seed, chain_offset, sweep_offset, tape, trace));
     }
     BARK_LAUNCH_CHECK();
     return BARK_OK;
@@ -439,7 +513,8 @@ int bark_mcmc_sweeps_timed(const bark_mcmc_dims* dims, void* workspace, bark_nod
     const size_t smem = sweep_smem_bytes((int)lay.L, (int)lay.d, (int)lay.P, (int)lay.wd);
     BARK_CHECK_ARG(smem <= 227 * 1024, "p_cap / n / d too large for the sweep kernel's shared memory");
     BARK_CUDA(cudaFuncSetAttribute(sweep_trees_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    BARK_CUDA(cudaFuncSetAttribute(hyper_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(la::Smem)));
+    BARK_CUDA(cudaFuncSetAttribute(hyper_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(la::Smem)));
+    BARK_CUDA(cudaFuncSetAttribute(hyper_refresh_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(la::Smem)));
     const int R = pick_cluster_size(dims->chains);
     std::vector<cudaEvent_t> ev((size_t)n_sweeps * 3);
     for (auto& e : ev) BARK_CUDA(cudaEventCreate(&e));
@@ -448,8 +523,7 @@ int bark_mcmc_sweeps_timed(const bark_mcmc_dims* dims, void* workspace, bark_nod
         BARK_CUDA(launch_sweep_trees(R, smem, st, lay, workspace, forest, *params, sidx, n_sweeps, seed, chain_offset,
                                      sweep_offset, nullptr, nullptr));
         BARK_CUDA(cudaEventRecord(ev[sidx * 3 + 1], st));
-        hyper_kernel<<<(unsigned)dims->chains, la::THREADS, sizeof(la::Smem), st>>>(lay, workspace, *params, sidx, n_sweeps,
-                                                                                  seed, chain_offset, sweep_offset, nullptr, nullptr);
+        BARK_CUDA(launch_hyper(st, lay, workspace, *params, sidx, n_sweeps, seed, chain_offset, sweep_offset, nullptr, nullptr));
         BARK_CUDA(cudaEventRecord(ev[sidx * 3 + 2], st));
     }
     BARK_LAUNCH_CHECK();

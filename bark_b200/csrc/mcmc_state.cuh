@@ -20,16 +20,19 @@ struct ChainScalars {
     double noise, scale, sig, c;
     double q, ldt, mll, yy;
     unsigned long long counters[16];
+    unsigned long long phase_cycles[12];  // BARK_PHASE_TIMING builds only: per-phase clock64 totals of the tree sweep
+    double prop_noise, prop_scale;  // accepted-but-not-yet-refreshed hyper proposal (hyper_eval -> hyper_refresh)
     int p_hi;           // used column extent (columns >= p_hi are free and identity-like)
     unsigned status;    // BARK_ST_* bits
-    int pad0, pad1;
+    int hyper_accept;   // set by hyper_eval_kernel, consumed by hyper_refresh_kernel
+    int pad1;
 };
 
 struct WsLayout {
     int64_t chains, n, d, m, L, P, wd, npad;
     size_t off_xt, off_y, off_bounds, off_ft;  // shared
     size_t off_chain0, chain_stride;           // per chain block
-    size_t off_binv, off_wk, off_a, off_bits, off_ck, off_gk, off_b, off_w, off_yv, off_colmap, off_colused, off_sc;
+    size_t off_binv, off_wk, off_a, off_bits, off_ck, off_gk, off_dg, off_b, off_w, off_yv, off_colmap, off_colused, off_sc;
     size_t total;
 };
 
@@ -54,6 +57,7 @@ __host__ __device__ inline WsLayout make_layout(const bark_mcmc_dims& dm) {
     w.off_bits = c;    c = align256(c + P * (size_t)w.wd * sizeof(uint32_t));
     w.off_ck = c;      c = align256(c + P * 64 * sizeof(double));
     w.off_gk = c;      c = align256(c + P * 64 * sizeof(double));
+    w.off_dg = c;      c = align256(c + 64 * 64 * sizeof(double));
     w.off_b = c;       c = align256(c + P * sizeof(double));
     w.off_w = c;       c = align256(c + P * sizeof(double));
     w.off_yv = c;      c = align256(c + P * sizeof(double));
@@ -66,7 +70,7 @@ __host__ __device__ inline WsLayout make_layout(const bark_mcmc_dims& dm) {
 }
 
 struct ChainView {
-    double* Binv; double* Wk; int32_t* A; uint32_t* bits; double* CK; double* GK;
+    double* Binv; double* Wk; int32_t* A; uint32_t* bits; double* CK; double* GK; double* DG;
     double* b; double* w; double* yv; uint16_t* colmap; uint32_t* colused; ChainScalars* sc;
 };
 
@@ -79,6 +83,7 @@ __host__ __device__ inline ChainView chain_view(const WsLayout& w, void* ws, int
     v.bits = (uint32_t*)(base + w.off_bits);
     v.CK = (double*)(base + w.off_ck);
     v.GK = (double*)(base + w.off_gk);
+    v.DG = (double*)(base + w.off_dg);
     v.b = (double*)(base + w.off_b);
     v.w = (double*)(base + w.off_w);
     v.yv = (double*)(base + w.off_yv);

@@ -12,7 +12,7 @@ struct MllScratch {
     double* yv;
 };
 
-__host__ __device__ inline size_t mll_scratch_doubles(int64_t n) { return (size_t)n * la::NB * 2 + (size_t)((n + 1) & ~1LL); }
+__host__ __device__ inline size_t mll_scratch_doubles(int64_t n) { return (size_t)n * la::NB * 2 + (size_t)la::NB * la::NB + (size_t)((n + 1) & ~1LL); }
 
 __global__ void __launch_bounds__(la::THREADS, 1)
 mll_batched_kernel(double* K, int n, const double* __restrict__ y, double* out_mll, double* out_logdet,
@@ -24,11 +24,12 @@ mll_batched_kernel(double* K, int n, const double* __restrict__ y, double* out_m
     double* base = scratch + b * mll_scratch_doubles(n);
     double* ck = base;
     double* gk = base + (size_t)n * la::NB;
-    double* yv = gk + (size_t)n * la::NB;
+    double* dg = gk + (size_t)n * la::NB;
+    double* yv = dg + (size_t)la::NB * la::NB;
     for (int i = threadIdx.x; i < n; i += la::THREADS) yv[i] = y[i];
     __syncthreads();
     double quad = 0.0;
-    const double logdet = la::block_sweep<false>(W, n, n, ck, gk, yv, &quad, s, status ? status + b : nullptr);
+    const double logdet = la::block_sweep<false>(W, n, n, ck, gk, dg, yv, &quad, s, status ? status + b : nullptr, la::SoloTeam());
     if (threadIdx.x == 0) {
         if (out_logdet) out_logdet[b] = logdet;
         if (out_quad) out_quad[b] = quad;

@@ -20,6 +20,19 @@ namespace bark {
 namespace cg = cooperative_groups;
 
 constexpr int SW_THREADS = 512;
+
+#ifdef BARK_PHASE_TIMING
+#define PHASE_MARK(i)                                        \
+    do {                                                     \
+        if (tid == 0) {                                      \
+            const long long now__ = clock64();               \
+            ph_acc[i] += (unsigned long long)(now__ - ph_t); \
+            ph_t = now__;                                    \
+        }                                                    \
+    } while (0)
+#else
+#define PHASE_MARK(i) do { } while (0)
+#endif
 constexpr int SW_MAX_R = 4;
 
 struct SweepCtl {  // small shared control block (kept identical on every CTA of the cluster)
@@ -102,8 +115,13 @@ sweep_trees_kernel(WsLayout lay, void* ws, bark_nodes_soa forest, bark_params pr
         tape ? ((size_t)(chain * n_sweeps_call + sweep_in_call)) * (size_t)(m * TAPE_PER_TREE + TAPE_PER_HYPER) : 0;
     double* trace_base = trace ? trace + ((size_t)(chain * n_sweeps_call + sweep_in_call)) * (size_t)(m + 1) * 3 : nullptr;
 
+#ifdef BARK_PHASE_TIMING
+    unsigned long long ph_acc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    long long ph_t = clock64();
+#endif
     for (int t = 0; t < m; ++t) {
         __syncthreads();
+        PHASE_MARK(11);
         // ---- stage the tree and the root box
         const int64_t g0 = (chain * (int64_t)m + t) * L;
         for (int e = tid; e < L; e += SW_THREADS) {
@@ -118,6 +136,7 @@ sweep_trees_kernel(WsLayout lay, void* ws, bark_nodes_soa forest, bark_params pr
         }
         for (int e = tid; e < 2 * d; e += SW_THREADS) box[e] = sv.bounds[e];
         __syncthreads();
+        PHASE_MARK(0);
 
         // ---- proposal (warp 0 of every CTA; identical inputs -> identical proposal)
         double u[6];
@@ -131,6 +150,7 @@ sweep_trees_kernel(WsLayout lay, void* ws, bark_nodes_soa forest, bark_params pr
             if (lane == 0) ctl->prop = p;
         }
         __syncthreads();
+        PHASE_MARK(1);
         const Prop p = ctl->prop;
         const double cur_q = ctl->q, cur_ldt = ctl->ldt, cur_mll = ctl->mll;
         const int p_hi = ctl->p_hi;
@@ -143,8 +163,8 @@ sweep_trees_kernel(WsLayout lay, void* ws, bark_nodes_soa forest, bark_params pr
         if (p.valid) {
             const int a = p.a, b = p.b;
             const int pe = max(p_hi, max(a, b) + 1);
-            pe64 = min(P, (pe + 63) & ~63);
-            const int share = pe64 / R;  // multiple of 16
+            pe64 = min(P, (pe + 15) & ~15);  // used extent, rounded to 16 columns
+            const int share = pe64 / R;      // multiple of 4
             r0 = cr * share;
             r1 = r0 + share;
             // ---- phase 1: moved-point masks u+ / u-, eta = u^T y, n_u = u^T u
@@ -179,6 +199,7 @@ sweep_trees_kernel(WsLayout lay, void* ws, bark_nodes_soa forest, bark_params pr
             }
             eta = block_sum(eta_part, red);
             n_u = block_sum((double)cnt_part, red);  // exact (integers < 2^53)
+            PHASE_MARK(2);
 
             // ---- phase 2: v = Z^T u for this CTA's columns [r0, r1): four threads per column, words striped
             for (int base = r0; base < r1; base += SW_THREADS / 4) {
@@ -208,7 +229,9 @@ sweep_trees_kernel(WsLayout lay, void* ws, bark_nodes_soa forest, bark_params pr
             const double* row_a = cv.Binv + (size_t)a * P;
             const double* row_b = cv.Binv + (size_t)b * P;
             for (int k = tid; k < pe64; k += SW_THREADS) Wd[k] = __ldcg(row_a + k) - __ldcg(row_b + k);
+            PHASE_MARK(3);
             cluster.sync();  // (1) all columns of v present everywhere
+            PHASE_MARK(4);
 
             // ---- phase 3: Wv = Binv v for this CTA's rows (closed form for prune: e_b - c Binv[:,b])
             if (p.move == MOVE_PRUNE) {
@@ -244,7 +267,9 @@ sweep_trees_kernel(WsLayout lay, void* ws, bark_nodes_soa forest, bark_params pr
                     }
                 }
             }
+            PHASE_MARK(5);
             cluster.sync();  // (2) all rows of Wv present everywhere
+            PHASE_MARK(6);
 
             // ---- phase 4: 2x2 capacitance matrix and the proposed log-MLL (identical on every CTA)
             double pvv = 0.0, pvw = 0.0;
@@ -285,14 +310,15 @@ sweep_trees_kernel(WsLayout lay, void* ws, bark_nodes_soa forest, bark_params pr
                 if (p.valid) {
                     ++n_valid;
                     ++n_valid_move[p.move];
-                    const unsigned long long nb64 = (unsigned long long)(pe64 / 64);
-                    if (p.move != MOVE_PRUNE) blk_eval += nb64 * nb64;
-                    if (accept) blk_upd += nb64 * nb64;
+                    const unsigned long long ext = (unsigned long long)pe64;
+                    if (p.move != MOVE_PRUNE) blk_eval += ext * ext;
+                    if (accept) blk_upd += ext * ext;
                     cols_scanned += (unsigned long long)pe64;
                 }
             }
         }
 
+        PHASE_MARK(7);
         if (accept) {
             __syncthreads();  // every thread of this CTA has finished reading w / Binv for the evaluation
             const int a = p.a, b = p.b;
@@ -402,9 +428,15 @@ sweep_trees_kernel(WsLayout lay, void* ws, bark_nodes_soa forest, bark_params pr
                 }
             }
         }
+        PHASE_MARK(8);
         if (p.valid) cluster.sync();  // (3) peer's global-memory edits visible; exchanged vectors free for reuse
     }
+    PHASE_MARK(9);
     __syncthreads();
+#ifdef BARK_PHASE_TIMING
+    if (tid == 0 && cr == 0)
+        for (int i = 0; i < 12; ++i) sc->phase_cycles[i] += ph_acc[i];
+#endif
     if (tid == 0 && cr == 0) {
         sc->q = ctl->q; sc->ldt = ctl->ldt; sc->mll = ctl->mll; sc->p_hi = ctl->p_hi;
         sc->counters[0] += (unsigned long long)m;
@@ -416,8 +448,8 @@ sweep_trees_kernel(WsLayout lay, void* ws, bark_nodes_soa forest, bark_params pr
         sc->counters[8] += n_valid_move[0];
         sc->counters[9] += n_valid_move[1];
         sc->counters[10] += n_valid_move[2];
-        sc->counters[11] += blk_eval;      // sum over matvec evaluations of (extent/64)^2
-        sc->counters[12] += blk_upd;       // sum over accepted updates of (extent/64)^2
+        sc->counters[11] += blk_eval;      // sum over matvec evaluations of extent^2
+        sc->counters[12] += blk_upd;       // sum over accepted updates of extent^2
         sc->counters[13] += cols_scanned;  // leaf-bitset columns scanned for v = Z^T u
     }
 }

@@ -243,10 +243,10 @@ def run_b200_arm(a, rank, local_rank, world):
     d2 = (ca - cb).sum(axis=0)
     wd = (n + 31) // 32
     # algorithmic bytes of the leaf-space formulation:
-    #   matvec evaluation: 8 B x extent^2          (read Binv once)            -> counters[11] * 4096 * 8
-    #   accepted update  : 16 B x extent^2         (read + write Binv once)    -> counters[12] * 4096 * 16
+    #   matvec evaluation: 8 B x extent^2          (read Binv once)            -> counters[11] * 8
+    #   accepted update  : 16 B x extent^2         (read + write Binv once)    -> counters[12] * 16
     #   v = Z^T u        : 4 B x wd x extent       (leaf bitsets)              -> counters[13] * wd * 4
-    alg_bytes = d2[11] * 4096 * 8 + d2[12] * 4096 * 16 + d2[13] * wd * 4
+    alg_bytes = d2[11] * 8 + d2[12] * 16 + d2[13] * wd * 4
     peak, peak_src = measured_peaks()
     ach = alg_bytes / (ms_trees / 1e3) / 1e9
     acc_rate = d2[2] / max(d2[0], 1)
@@ -301,7 +301,7 @@ def run_b200_arm(a, rank, local_rank, world):
                             "sample": f"failed: {type(exc).__name__}: {exc}"}
 
     if rank == 0:
-        ws_mb = C * (float(np.mean(((p_used + 63) // 64 * 64) ** 2)) * 8 + float(np.mean(p_used)) * wd * 4) / 1e6
+        ws_mb = C * (float(np.mean(((p_used + 15) // 16 * 16) ** 2)) * 8 + float(np.mean(p_used)) * wd * 4) / 1e6
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": ms_total / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

@@ -144,7 +144,7 @@ int bark_mcmc_sweeps_timed(const bark_mcmc_dims* dims, void* workspace, bark_nod
 
 /* Read-out of per-chain scalars: each (chains) or NULL.  counters (chains, 16) u64:
  * [0 tree proposals issued, 1 valid, 2 accepted, 3 hyper issued, 4 hyper accepted, 5-7 grow/prune/change accepted,
- *  8-10 grow/prune/change valid, 11 sum (extent/64)^2 over matvec evaluations, 12 same over accepted updates,
+ *  8-10 grow/prune/change valid, 11 sum of extent^2 over matvec evaluations, 12 same over accepted updates,
  *  13 leaf-bitset columns scanned, 14-15 reserved]. */
 int bark_mcmc_read(const bark_mcmc_dims* dims, const void* workspace, double* noise, double* scale, double* mll,
                    uint32_t* status, uint64_t* counters, int32_t* p_used, void* stream);
