@@ -378,7 +378,10 @@ __global__ void mcmc_export_kernel(WsLayout lay, const void* ws, int64_t chain, 
     const int64_t PP = lay.P * lay.P;
     for (int64_t e = tid; e < PP; e += nth) {
         if (A) A[e] = cv.A[e];
-        if (Binv) Binv[e] = cv.Binv[e];
+        if (Binv) {  // the sampler keeps only the lower triangle current: export the symmetric matrix
+            const int64_t r = e / lay.P, c = e % lay.P;
+            Binv[e] = (c <= r) ? cv.Binv[e] : cv.Binv[c * lay.P + r];
+        }
     }
     if (colmap)
         for (int64_t e = tid; e < lay.m * lay.L; e += nth) colmap[e] = cv.colmap[e] == NO_COL ? -1 : (int32_t)cv.colmap[e];
@@ -431,14 +434,24 @@ static cudaError_t launch_hyper(cudaStream_t st, const WsLayout& lay, void* ws, 
     return cudaLaunchKernelEx(&cfg, hyper_refresh_kernel, lay, ws);
 }
 
-static cudaError_t launch_sweep_trees(int R, size_t smem, cudaStream_t st, const WsLayout& lay, void* ws,
-                                      bark_nodes_soa forest, const bark_params& prm, int64_t sidx, int64_t n_sweeps,
-                                      uint64_t seed, int64_t chain_offset, int64_t sweep_offset, const double* tape,
-                                      double* trace) {
+static size_t sweep_smem_budget() {
+    int dev = 0, optin = 227 * 1024;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    return (size_t)std::min(optin, 227 * 1024);
+}
+
+static cudaError_t launch_sweep_trees(int R, cudaStream_t st, const WsLayout& lay, void* ws, bark_nodes_soa forest,
+                                      const bark_params& prm, int64_t sidx, int64_t n_sweeps, uint64_t seed,
+                                      int64_t chain_offset, int64_t sweep_offset, const double* tape, double* trace) {
+    const size_t budget = sweep_smem_budget();
+    const SweepSmemLayout sl = sweep_smem_layout((int)lay.L, (int)lay.d, (int)lay.P, (int)lay.wd, budget);
+    if (sl.total > budget) return cudaErrorInvalidValue;
+    cudaError_t e = cudaFuncSetAttribute(sweep_trees_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sl.total);
+    if (e != cudaSuccess) return e;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(lay.chains * R));
     cfg.blockDim = dim3(SW_THREADS);
-    cfg.dynamicSmemBytes = smem;
+    cfg.dynamicSmemBytes = sl.total;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -448,7 +461,7 @@ static cudaError_t launch_sweep_trees(int R, size_t smem, cudaStream_t st, const
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     return cudaLaunchKernelEx(&cfg, sweep_trees_kernel, lay, ws, forest, prm, sidx, n_sweeps, seed, chain_offset,
-                              sweep_offset, tape, trace);
+                              sweep_offset, tape, trace, budget);
 }
 
 }  // namespace bark
@@ -487,14 +500,16 @@ int bark_mcmc_sweeps(const bark_mcmc_dims* dims, void* workspace, bark_nodes_soa
     BARK_CHECK_ARG(n_sweeps >= 0, "n_sweeps < 0");
     const WsLayout lay = make_layout(*dims);
     cudaStream_t st = (cudaStream_t)stream;
-    const size_t smem = sweep_smem_bytes((int)lay.L, (int)lay.d, (int)lay.P, (int)lay.wd);
-    BARK_CHECK_ARG(smem <= 227 * 1024, "p_cap / n / d too large for the sweep kernel's shared memory");
-    BARK_CUDA(cudaFuncSetAttribute(sweep_trees_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    {
+        const size_t budget = sweep_smem_budget();
+        BARK_CHECK_ARG(sweep_smem_layout((int)lay.L, (int)lay.d, (int)lay.P, (int)lay.wd, budget).total <= budget,
+                       "p_cap / n / d too large for the sweep kernel's shared memory");
+    }
     BARK_CUDA(cudaFuncSetAttribute(hyper_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(la::Smem)));
     BARK_CUDA(cudaFuncSetAttribute(hyper_refresh_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(la::Smem)));
     const int R = pick_cluster_size(dims->chains);
     for (int64_t sidx = 0; sidx < n_sweeps; ++sidx) {
-        BARK_CUDA(launch_sweep_trees(R, smem, st, lay, workspace, forest, *params, sidx, n_sweeps, seed, chain_offset,
+        BARK_CUDA(launch_sweep_trees(R, st, lay, workspace, forest, *params, sidx, n_sweeps, seed, chain_offset,
                                      sweep_offset, tape, trace));
         BARK_CUDA(launch_hyper(st, lay, workspace, *params, sidx, n_sweeps, seed, chain_offset, sweep_offset, tape, trace));
     }
@@ -510,9 +525,11 @@ int bark_mcmc_sweeps_timed(const bark_mcmc_dims* dims, void* workspace, bark_nod
     BARK_CHECK_ARG(n_sweeps >= 1 && n_sweeps <= 4096, "n_sweeps out of range (1..4096)");
     const WsLayout lay = make_layout(*dims);
     cudaStream_t st = (cudaStream_t)stream;
-    const size_t smem = sweep_smem_bytes((int)lay.L, (int)lay.d, (int)lay.P, (int)lay.wd);
-    BARK_CHECK_ARG(smem <= 227 * 1024, "p_cap / n / d too large for the sweep kernel's shared memory");
-    BARK_CUDA(cudaFuncSetAttribute(sweep_trees_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    {
+        const size_t budget = sweep_smem_budget();
+        BARK_CHECK_ARG(sweep_smem_layout((int)lay.L, (int)lay.d, (int)lay.P, (int)lay.wd, budget).total <= budget,
+                       "p_cap / n / d too large for the sweep kernel's shared memory");
+    }
     BARK_CUDA(cudaFuncSetAttribute(hyper_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(la::Smem)));
     BARK_CUDA(cudaFuncSetAttribute(hyper_refresh_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(la::Smem)));
     const int R = pick_cluster_size(dims->chains);
@@ -520,7 +537,7 @@ int bark_mcmc_sweeps_timed(const bark_mcmc_dims* dims, void* workspace, bark_nod
     for (auto& e : ev) BARK_CUDA(cudaEventCreate(&e));
     for (int64_t sidx = 0; sidx < n_sweeps; ++sidx) {
         BARK_CUDA(cudaEventRecord(ev[sidx * 3 + 0], st));
-        BARK_CUDA(launch_sweep_trees(R, smem, st, lay, workspace, forest, *params, sidx, n_sweeps, seed, chain_offset,
+        BARK_CUDA(launch_sweep_trees(R, st, lay, workspace, forest, *params, sidx, n_sweeps, seed, chain_offset,
                                      sweep_offset, nullptr, nullptr));
         BARK_CUDA(cudaEventRecord(ev[sidx * 3 + 1], st));
         BARK_CUDA(launch_hyper(st, lay, workspace, *params, sidx, n_sweeps, seed, chain_offset, sweep_offset, nullptr, nullptr));

@@ -69,10 +69,14 @@ predict_sample_kernel(WsLayout lay, const void* ws, const WalkNode* __restrict__
     const double* __restrict__ Binv = cv.Binv;
     double dg = 0.0, off = 0.0;
     for (int t = 0; t < m; ++t) {
-        const double* row = Binv + (size_t)cols[(size_t)t * PR_THREADS + threadIdx.x] * P;
-        dg += row[cols[(size_t)t * PR_THREADS + threadIdx.x]];
+        // only the lower triangle of Binv is kept current by the sampler: index (max, min)
+        const int ci = cols[(size_t)t * PR_THREADS + threadIdx.x];
+        dg += Binv[(size_t)ci * P + ci];
         double part = 0.0;
-        for (int t2 = 0; t2 < t; ++t2) part += row[cols[(size_t)t2 * PR_THREADS + threadIdx.x]];
+        for (int t2 = 0; t2 < t; ++t2) {
+            const int cj = cols[(size_t)t2 * PR_THREADS + threadIdx.x];
+            part += Binv[(size_t)max(ci, cj) * P + min(ci, cj)];
+        }
         off += part;
     }
     const int64_t o = sample * n_c + p0 + threadIdx.x;

@@ -98,10 +98,27 @@ __device__ __forceinline__ double log_prior_ratio_at_depth(uint32_t depth, doubl
 //   u[0..3]  : uniforms (move type, node, feature, rule)
 //   box      : shared-memory scratch, 2*d doubles, pre-filled with `bounds`
 //   cm       : this tree's leaf -> column map;   colused / P: column allocator bitmap / capacity
+//   logtab[k] = log(k), k <= L+1;  priortab[dep] = log_prior_ratio_at_depth(dep): precomputed once per launch
 __device__ __forceinline__ Prop propose_tree_warp(const TreeSmem& T, int L, double* box, const int32_t* ft, int d,
                                                   const uint16_t* cm, const uint32_t* colused, int P,
-                                                  const bark_params& prm, const double* u, unsigned* status) {
+                                                  const bark_params& prm, const double* u, unsigned* status,
+                                                  const double* logtab, const double* priortab) {
     const int lane = threadIdx.x & 31;
+    // lowest free leaf column (needed by grow), found by the whole warp: P/32 <= 256 words, 8 per lane at most
+    int fcol = -1;
+    {
+        const int nwords = P / 32;
+        for (int base = 0; base < nwords && fcol < 0; base += 32) {
+            const int w = base + lane;
+            const uint32_t fr = (w < nwords) ? ~colused[w] : 0u;
+            const unsigned has = __ballot_sync(0xffffffffu, fr != 0u);
+            if (has) {
+                const int src = __ffs(has) - 1;
+                const uint32_t word = __shfl_sync(0xffffffffu, fr, src);
+                fcol = (base + src) * 32 + __ffs(word) - 1;
+            }
+        }
+    }
     const int nch = (L + 31) >> 5;
     uint32_t mT[8], mS[8], mI[8];
     int nT = 0, nS = 0;
@@ -210,7 +227,7 @@ __device__ __forceinline__ Prop propose_tree_warp(const TreeSmem& T, int L, doub
         if ((double)thr32 == hi && ft[f] == FEAT_INT) return p;
     }
 
-    const uint32_t depth = T.depth[node];
+    const uint32_t depth = min(T.depth[node], (uint32_t)L);  // index into the per-depth prior table
     if (move == MOVE_GROW) {
         // first two inactive slots in ascending order (tree_proposals.py:45-58)
         int s0 = -1, s1 = -1;
@@ -226,12 +243,7 @@ __device__ __forceinline__ Prop propose_tree_warp(const TreeSmem& T, int L, doub
             atomicOr(status, BARK_ST_TREE_OVERFLOW);
             return p;
         }
-        // free leaf column for the right child (lowest index first)
-        int fcol = -1;
-        for (int w = 0; w < P / 32 && fcol < 0; ++w) {
-            const uint32_t fr = ~__ldcg(colused + w);
-            if (fr) fcol = w * 32 + __ffs(fr) - 1;
-        }
+        // free leaf column for the right child (lowest index first; found above by the whole warp)
         if (fcol < 0) {
             atomicOr(status, BARK_ST_COL_OVERFLOW);
             return p;
@@ -242,17 +254,17 @@ __device__ __forceinline__ Prop propose_tree_warp(const TreeSmem& T, int L, doub
             was_sing = (mS[up >> 5] >> (up & 31)) & 1u;
         }
         const int w1 = nS - was_sing + 1;  // singly-internal nodes after the grow (tree_proposals.py:104-107)
-        const double log_q = __dsub_rn(log((double)nT), log((double)w1));
-        p.lqp = __dadd_rn(log_q, log_prior_ratio_at_depth(depth, prm.alpha, prm.beta));
+        const double log_q = __dsub_rn(logtab[nT], logtab[w1]);
+        p.lqp = __dadd_rn(log_q, priortab[depth]);
         p.sl = s0; p.sr = s1;
-        p.a = fcol; p.b = (int)__ldcg(cm + node);
+        p.a = fcol; p.b = (int)cm[node];
     } else {
         p.sl = (int)T.left[node];
         p.sr = (int)T.right[node];
-        const int pL = (int)__ldcg(cm + p.sl), pR = (int)__ldcg(cm + p.sr);
+        const int pL = (int)cm[p.sl], pR = (int)cm[p.sr];
         if (move == MOVE_PRUNE) {
-            const double log_q = __dsub_rn(log((double)nS), log((double)(nT - 1)));  // :111-114
-            p.lqp = __dadd_rn(log_q, -log_prior_ratio_at_depth(depth, prm.alpha, prm.beta));
+            const double log_q = __dsub_rn(logtab[nS], logtab[nT - 1]);  // :111-114
+            p.lqp = __dadd_rn(log_q, -priortab[depth]);
             p.a = pL; p.b = pR;
         } else {
             p.lqp = 0.0;

@@ -1,13 +1,20 @@
 // Tree sweep: the m tree MH steps of one sweep of one chain (bark_sampler.py:233-264) in leaf space.
 //
-// A thread-block CLUSTER of R CTAs (R = 1, 2 or 4; 512 threads each) owns one chain, so that 64 chains fill
-// 128 of the 148 SMs.  B^-1 stays in global memory (L2/HBM) and is split by rows across the cluster:
+// A thread-block CLUSTER of R CTAs (R = 1 or 2; 512 threads each) owns one chain, so that 64 chains fill
+// 128 of the 148 SMs.  Only the LOWER TRIANGLE of the symmetric B^-1 is kept current (row q holds columns 0..q),
+// which halves the bytes per pass and lets 64 chains' states (~55 MB) stay L2-resident.  Rows are interleaved
+// across the cluster (row q belongs to CTA q % R):
 //   phase 1  moved-point masks u+/u-, eta = u^T y, n_u           (redundant on every CTA; N bits)
 //   phase 2  v = Z^T u by AND+POPC over the leaf bitsets         (columns split; halves exchanged through DSMEM)
-//   phase 3  Wd = Binv d (two rows), Wv = Binv v                 (rows split; halves exchanged through DSMEM)
+//   phase 3  Wd = Binv d (two rows), Wv = Binv v: every streamed row prefix yields a dot product (row part)
+//            and an axpy into per-lane column accumulators (column part); partial vectors summed over the cluster
 //   phase 4  2x2 capacitance matrix, proposed log-MLL, MH accept (redundant, bitwise identical on every CTA)
-//   accept   symmetric rank-2 update of the CTA's rows of Binv, w; integer A / bitsets / forest edits
-// Memory phases keep 16 independent 16-byte loads in flight per lane (two rows x eight column chunks).
+//   accept   symmetric rank-2 update of the CTA's rows of Binv; w; integer A / bitsets / forest edits
+//
+// The two HBM/L2-bound passes over B^-1 (matvec, rank-2 update) stream the CTA's rows through a shared-memory
+// ring with the bulk-copy engine (TMA, cp.async.bulk + mbarrier full/empty pairs): one producer warp keeps up
+// to ~170 KB of row copies in flight, 15 consumer warps reduce (or update and bulk-store back) one row each.
+// That lifts the per-SM request-tracking limit of plain loads (ncu: 29 % of DRAM peak, long-scoreboard bound).
 // State written by a peer CTA is only read after a cluster barrier (release/acquire) and through L2 (.cg).
 #pragma once
 #include <cooperative_groups.h>
@@ -20,6 +27,11 @@ namespace bark {
 namespace cg = cooperative_groups;
 
 constexpr int SW_THREADS = 512;
+constexpr int SW_WARPS = SW_THREADS / 32;
+constexpr int SW_MAX_R = 2;
+constexpr int SW_PROD_WARP = SW_WARPS - 1;  // bulk-copy producer
+constexpr int SW_NCW = SW_WARPS - 1;        // consumer warps
+constexpr int SW_NSLOT_MAX = 64;
 
 #ifdef BARK_PHASE_TIMING
 #define PHASE_MARK(i)                                        \
@@ -33,7 +45,52 @@ constexpr int SW_THREADS = 512;
 #else
 #define PHASE_MARK(i) do { } while (0)
 #endif
-constexpr int SW_MAX_R = 4;
+
+// ---------------------------------------------------------------- mbarrier / bulk-copy (TMA) primitives
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.b32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// Warp-uniform wait: every lane of the calling warp waits on the SAME barrier (no divergence inside).
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {
+    }
+}
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void* gdst, const void* smem_src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(smem_src)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 
 struct SweepCtl {  // small shared control block (kept identical on every CTA of the cluster)
     Prop prop;
@@ -41,72 +98,137 @@ struct SweepCtl {  // small shared control block (kept identical on every CTA of
     int p_hi;
 };
 
-__host__ __device__ inline size_t sweep_smem_bytes(int L, int d, int P, int wd) {
+struct SweepSmemLayout {
+    size_t off_ctl, off_leaf, off_u32, off_cm, off_box, off_ft, off_vd, off_wd, off_wv, off_ws, off_upos, off_uneg, off_red,
+        off_logtab, off_priortab, off_colused, off_bars, off_ydot, off_parts, off_ypart, off_ring, ring_bytes, total;
+};
+__host__ __device__ inline SweepSmemLayout sweep_smem_layout(int L, int d, int P, int wd, size_t budget) {
+    SweepSmemLayout s;
     size_t o = 0;
-    o += align256(sizeof(SweepCtl));
-    o += align256((size_t)L * 2);        // is_leaf, active
-    o += align256((size_t)L * 4 * 6);    // feat,left,right,parent,depth,thr
-    o += align256((size_t)d * 2 * 8);    // box
-    o += align256((size_t)d * 4);        // ft
-    o += align256((size_t)P * 8) * 3;    // vd, Wd, Wv
-    o += align256((size_t)wd * 4) * 2;   // upos, uneg
-    o += align256(64 * 8);               // red
-    return o;
+    s.off_ctl = o;      o += align256(sizeof(SweepCtl));
+    s.off_leaf = o;     o += align256((size_t)L * 2);          // is_leaf, active
+    s.off_u32 = o;      o += align256((size_t)L * 4 * 6);      // feat,left,right,parent,depth,thr
+    s.off_cm = o;       o += align256((size_t)L * 2);          // this tree's leaf -> column map
+    s.off_box = o;      o += align256((size_t)d * 2 * 8);
+    s.off_ft = o;       o += align256((size_t)d * 4);
+    s.off_vd = o;       o += align256((size_t)P * 8);
+    s.off_wd = o;       o += align256((size_t)P * 8);
+    s.off_wv = o;       o += align256((size_t)P * 8);
+    s.off_ws = o;       o += align256((size_t)P * 8);          // w = Binv b (full copy per CTA)
+    s.off_upos = o;     o += align256((size_t)wd * 4);
+    s.off_uneg = o;     o += align256((size_t)wd * 4);
+    s.off_red = o;      o += align256(80 * 8);
+    s.off_logtab = o;   o += align256((size_t)(L + 2) * 8);
+    s.off_priortab = o; o += align256((size_t)(L + 1) * 8);
+    s.off_colused = o;  o += align256((size_t)(P / 32) * 4);
+    s.off_bars = o;     o += align256((size_t)SW_NSLOT_MAX * 2 * 8);
+    s.off_ydot = o;     o += align256((size_t)P * 8);                    // row-dot part of the symmetric matvec
+    s.off_parts = o;    o += align256((size_t)P * 8) * SW_MAX_R;         // per-CTA partial vectors (DSMEM targets)
+    s.off_ypart = o;    o += align256((size_t)SW_NCW * 512 * 8);         // per-warp column accumulators of a panel
+    o = (o + 1023) & ~(size_t)1023;
+    s.off_ring = o;
+    s.ring_bytes = (budget > o + 1024) ? ((budget - o) & ~(size_t)1023) : 0;
+    if (s.ring_bytes > 176 * 1024) s.ring_bytes = 176 * 1024;
+    s.total = o + s.ring_bytes;
+    return s;
 }
 
-__device__ __forceinline__ double2 ldcg2(const double* p) {
-    return __ldcg(reinterpret_cast<const double2*>(p));
+__device__ __forceinline__ double2 ldcg2(const double* p) { return __ldcg(reinterpret_cast<const double2*>(p)); }
+
+// deterministic block-wide sum of two values at once (one barrier pair)
+__device__ __forceinline__ void block_sum2(double& a, double& b, double* scratch) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    a = warp_sum(a);
+    b = warp_sum(b);
+    __syncthreads();
+    if (lane == 0) { scratch[wid] = a; scratch[32 + wid] = b; }
+    __syncthreads();
+    const double ra = (lane < SW_WARPS) ? scratch[lane] : 0.0;
+    const double rb = (lane < SW_WARPS) ? scratch[32 + lane] : 0.0;
+    a = warp_sum(ra);
+    b = warp_sum(rb);
 }
 
 __global__ void __launch_bounds__(SW_THREADS, 1)
 sweep_trees_kernel(WsLayout lay, void* ws, bark_nodes_soa forest, bark_params prm, int64_t sweep_in_call,
                    int64_t n_sweeps_call, uint64_t seed, int64_t chain_offset, int64_t sweep_offset,
-                   const double* __restrict__ tape, double* __restrict__ trace) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+                   const double* __restrict__ tape, double* __restrict__ trace, size_t smem_budget) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
     cg::cluster_group cluster = cg::this_cluster();
     const int R = (int)cluster.num_blocks(), cr = (int)cluster.block_rank();
 
     const int P = (int)lay.P, L = (int)lay.L, m = (int)lay.m, n = (int)lay.n, wd = (int)lay.wd, npad = (int)lay.npad;
     const int d = (int)lay.d;
-    unsigned char* sp = smem_raw;
-    SweepCtl* ctl = (SweepCtl*)sp;           sp += align256(sizeof(SweepCtl));
+    const SweepSmemLayout sl = sweep_smem_layout(L, d, P, wd, smem_budget);
+    SweepCtl* ctl = (SweepCtl*)(smem_raw + sl.off_ctl);
     TreeSmem T;
-    T.is_leaf = sp; T.active = sp + L;       sp += align256((size_t)L * 2);
-    T.feat = (uint32_t*)sp; T.left = T.feat + L; T.right = T.left + L; T.parent = T.right + L; T.depth = T.parent + L;
-    T.thr = (float*)(T.depth + L);           sp += align256((size_t)L * 4 * 6);
-    double* box = (double*)sp;               sp += align256((size_t)d * 2 * 8);
-    int32_t* ftc = (int32_t*)sp;             sp += align256((size_t)d * 4);
-    double* vd = (double*)sp;                sp += align256((size_t)P * 8);
-    double* Wd = (double*)sp;                sp += align256((size_t)P * 8);
-    double* Wv = (double*)sp;                sp += align256((size_t)P * 8);
-    uint32_t* upos = (uint32_t*)sp;          sp += align256((size_t)wd * 4);
-    uint32_t* uneg = (uint32_t*)sp;          sp += align256((size_t)wd * 4);
-    double* red = (double*)sp;
+    T.is_leaf = smem_raw + sl.off_leaf; T.active = T.is_leaf + L;
+    T.feat = (uint32_t*)(smem_raw + sl.off_u32); T.left = T.feat + L; T.right = T.left + L; T.parent = T.right + L;
+    T.depth = T.parent + L; T.thr = (float*)(T.depth + L);
+    uint16_t* cm_s = (uint16_t*)(smem_raw + sl.off_cm);
+    double* box = (double*)(smem_raw + sl.off_box);
+    int32_t* ftc = (int32_t*)(smem_raw + sl.off_ft);
+    double* vd = (double*)(smem_raw + sl.off_vd);
+    double* Wd = (double*)(smem_raw + sl.off_wd);
+    double* Wv = (double*)(smem_raw + sl.off_wv);
+    double* w_s = (double*)(smem_raw + sl.off_ws);
+    uint32_t* upos = (uint32_t*)(smem_raw + sl.off_upos);
+    uint32_t* uneg = (uint32_t*)(smem_raw + sl.off_uneg);
+    double* red = (double*)(smem_raw + sl.off_red);
+    double* logtab = (double*)(smem_raw + sl.off_logtab);
+    double* priortab = (double*)(smem_raw + sl.off_priortab);
+    uint32_t* colused_s = (uint32_t*)(smem_raw + sl.off_colused);
+    uint64_t* full_bar = (uint64_t*)(smem_raw + sl.off_bars);
+    uint64_t* empty_bar = full_bar + SW_NSLOT_MAX;
+    double* ydot = (double*)(smem_raw + sl.off_ydot);
+    double* parts = (double*)(smem_raw + sl.off_parts);
+    double* ypart = (double*)(smem_raw + sl.off_ypart);
+    unsigned char* ring = smem_raw + sl.off_ring;
+    const size_t parts_stride = align256((size_t)P * 8) / 8;
 
     // peers' copies of the exchanged vectors (distributed shared memory)
     double* vd_peer[SW_MAX_R];
-    double* Wv_peer[SW_MAX_R];
+    double* parts_peer[SW_MAX_R];  // this CTA's slot (index cr) inside every CTA's `parts`
 #pragma unroll
     for (int r = 0; r < SW_MAX_R; ++r) {
         vd_peer[r] = (r < R) ? cluster.map_shared_rank(vd, r) : vd;
-        Wv_peer[r] = (r < R) ? cluster.map_shared_rank(Wv, r) : Wv;
+        parts_peer[r] = ((r < R) ? cluster.map_shared_rank(parts, r) : parts) + (size_t)cr * parts_stride;
     }
 
     const int64_t chain = blockIdx.x / R;
     ChainView cv = chain_view(lay, ws, chain);
     SharedView sv = shared_view(lay, ws);
     ChainScalars* sc = cv.sc;
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = SW_THREADS >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
 
     // a dead chain (status set by an earlier launch) is skipped by the whole cluster
     if (__ldcg(&sc->status) & (BARK_ST_COL_OVERFLOW | BARK_ST_TREE_OVERFLOW | BARK_ST_HYPER_MODE)) return;
 
     const double sig = sc->sig, c = sc->c, yy = sc->yy;
     const double nlogsig = (double)n * log(sig);
+    const int p_hi_start = sc->p_hi;
     if (tid == 0) {
-        ctl->q = sc->q; ctl->ldt = sc->ldt; ctl->mll = sc->mll; ctl->p_hi = sc->p_hi;
+        ctl->q = sc->q; ctl->ldt = sc->ldt; ctl->mll = sc->mll; ctl->p_hi = p_hi_start;
     }
     for (int e = tid; e < d; e += SW_THREADS) ftc[e] = sv.ft[e];
+    for (int e = tid; e < L + 2; e += SW_THREADS) logtab[e] = log((double)e);
+    for (int e = tid; e < L + 1; e += SW_THREADS) priortab[e] = log_prior_ratio_at_depth((uint32_t)e, prm.alpha, prm.beta);
+    for (int e = tid; e < P / 32; e += SW_THREADS) colused_s[e] = __ldcg(cv.colused + e);
+    for (int e = tid; e < P; e += SW_THREADS) w_s[e] = __ldcg(cv.w + e);
+
+    // ring geometry for this launch: one slot per row of Binv, sized for the extent at launch + head-room
+    const int slot_cols = min(512, min(P, ((p_hi_start + 64) + 15) & ~15));  // a slot holds one row segment
+    const uint32_t slot_bytes = (uint32_t)slot_cols * 8u;
+    const int nslot = (int)min((size_t)SW_NSLOT_MAX, sl.ring_bytes / slot_bytes);
+    const bool ring_ok = nslot >= 4;
+    const int npl = max(1, min(32, nslot / 2));  // producer lanes
+    if (tid == 0 && ring_ok) {
+        for (int i = 0; i < nslot; ++i) { mbar_init(full_bar + i, 1); mbar_init(empty_bar + i, 1); }
+        fence_mbar_init();
+    }
+    fence_proxy_async();  // state written with generic stores by earlier kernels -> later bulk (async proxy) reads
+    uint32_t ring_base = 0;  // rows streamed so far (identical on every thread)
+
     unsigned long long n_valid = 0, n_acc = 0, n_acc_move[3] = {0, 0, 0}, n_valid_move[3] = {0, 0, 0};  // thread 0
     unsigned long long blk_eval = 0, blk_upd = 0, cols_scanned = 0;
 
@@ -122,7 +244,7 @@ sweep_trees_kernel(WsLayout lay, void* ws, bark_nodes_soa forest, bark_params pr
     for (int t = 0; t < m; ++t) {
         __syncthreads();
         PHASE_MARK(11);
-        // ---- stage the tree and the root box
+        // ---- stage the tree, its column map and the root box
         const int64_t g0 = (chain * (int64_t)m + t) * L;
         for (int e = tid; e < L; e += SW_THREADS) {
             T.is_leaf[e] = __ldcg(forest.is_leaf + g0 + e);
@@ -133,6 +255,7 @@ sweep_trees_kernel(WsLayout lay, void* ws, bark_nodes_soa forest, bark_params pr
             T.parent[e] = __ldcg(forest.parent + g0 + e);
             T.depth[e] = __ldcg(forest.depth + g0 + e);
             T.thr[e] = __ldcg(forest.threshold + g0 + e);
+            cm_s[e] = __ldcg(cv.colmap + (size_t)t * L + e);
         }
         for (int e = tid; e < 2 * d; e += SW_THREADS) box[e] = sv.bounds[e];
         __syncthreads();
@@ -146,7 +269,7 @@ sweep_trees_kernel(WsLayout lay, void* ws, bark_nodes_soa forest, bark_params pr
             rng_uniforms(seed, g_chain, g_sweep, (uint32_t)t, TAPE_PER_TREE, u);
         }
         if (wid == 0) {
-            Prop p = propose_tree_warp(T, L, box, ftc, d, cv.colmap + (size_t)t * L, cv.colused, P, prm, u, &sc->status);
+            Prop p = propose_tree_warp(T, L, box, ftc, d, cm_s, colused_s, P, prm, u, &sc->status, logtab, priortab);
             if (lane == 0) ctl->prop = p;
         }
         __syncthreads();
@@ -157,19 +280,19 @@ sweep_trees_kernel(WsLayout lay, void* ws, bark_nodes_soa forest, bark_params pr
 
         double new_q = cur_q, new_ldt = cur_ldt, new_mll = cur_mll;
         double eta = 0.0, n_u = 0.0, M00 = 0.0, M01 = 0.0, M11 = 0.0, det = -1.0, Ur0 = 0.0, Ur1 = 0.0;
-        int pe64 = 0, r0 = 0, r1 = 0;
+        int pe16 = 0, r0 = 0, r1 = 0;
         bool accept = false;
+        const bool use_ring = ring_ok;
 
         if (p.valid) {
             const int a = p.a, b = p.b;
             const int pe = max(p_hi, max(a, b) + 1);
-            pe64 = min(P, (pe + 15) & ~15);  // used extent, rounded to 16 columns
-            const int share = pe64 / R;      // multiple of 4
+            pe16 = min(P, (pe + 15) & ~15);  // used extent, rounded to 16 columns
+            const int share = pe16 / R;      // multiple of 4
             r0 = cr * share;
             r1 = r0 + share;
             // ---- phase 1: moved-point masks u+ / u-, eta = u^T y, n_u = u^T u
-            double eta_part = 0.0;
-            int cnt_part = 0;
+            double eta_part = 0.0, cnt_part = 0.0;
             const uint32_t* bits_a = cv.bits + (size_t)a * wd;
             const uint32_t* bits_b = cv.bits + (size_t)b * wd;
             const double* xf = sv.Xt + (size_t)p.feat * npad;
@@ -191,14 +314,15 @@ sweep_trees_kernel(WsLayout lay, void* ws, bark_nodes_soa forest, bark_params pr
                             neg = in_a && gl;
                         }
                     }
-                    if (pos) { eta_part += sv.y[i]; ++cnt_part; }
-                    if (neg) { eta_part -= sv.y[i]; ++cnt_part; }
+                    if (pos) { eta_part += sv.y[i]; cnt_part += 1.0; }
+                    if (neg) { eta_part -= sv.y[i]; cnt_part += 1.0; }
                 }
                 const unsigned bp = __ballot_sync(0xffffffffu, pos), bn = __ballot_sync(0xffffffffu, neg);
                 if (lane == 0) { upos[w] = bp; uneg[w] = bn; }
             }
-            eta = block_sum(eta_part, red);
-            n_u = block_sum((double)cnt_part, red);  // exact (integers < 2^53)
+            block_sum2(eta_part, cnt_part, red);  // counts are exact (integers < 2^53)
+            eta = eta_part;
+            n_u = cnt_part;
             PHASE_MARK(2);
 
             // ---- phase 2: v = Z^T u for this CTA's columns [r0, r1): four threads per column, words striped
@@ -225,63 +349,130 @@ sweep_trees_kernel(WsLayout lay, void* ws, bark_nodes_soa forest, bark_params pr
                         if (r < R) vd_peer[r][q] = val;
                 }
             }
-            // Wd = Binv d: rows a and b (every CTA reads the two full rows)
-            const double* row_a = cv.Binv + (size_t)a * P;
-            const double* row_b = cv.Binv + (size_t)b * P;
-            for (int k = tid; k < pe64; k += SW_THREADS) Wd[k] = __ldcg(row_a + k) - __ldcg(row_b + k);
+            // Wd = Binv d: rows a and b of the symmetric matrix (row prefix + column below the diagonal);
+            // prune also takes its closed form Wv = e_b - c Binv[:,b] from the same loads
+            for (int k = tid; k < pe16; k += SW_THREADS) {
+                const double sa = __ldcg(cv.Binv + ((k <= a) ? ((size_t)a * P + k) : ((size_t)k * P + a)));
+                const double sb = __ldcg(cv.Binv + ((k <= b) ? ((size_t)b * P + k) : ((size_t)k * P + b)));
+                Wd[k] = sa - sb;
+                if (p.move == MOVE_PRUNE) Wv[k] = ((k == b) ? 1.0 : 0.0) - c * sb;
+                ydot[k] = 0.0;
+            }
             PHASE_MARK(3);
             cluster.sync();  // (1) all columns of v present everywhere
             PHASE_MARK(4);
 
-            // ---- phase 3: Wv = Binv v for this CTA's rows (closed form for prune: e_b - c Binv[:,b])
-            if (p.move == MOVE_PRUNE) {
-                for (int k = tid; k < pe64; k += SW_THREADS) Wv[k] = ((k == b) ? 1.0 : 0.0) - c * __ldcg(row_b + k);
-            } else {
-                for (int q = r0 + 2 * wid; q < r1; q += 2 * nw) {
-                    const double* rowA = cv.Binv + (size_t)q * P;
-                    const double* rowB = rowA + P;
-                    double accA = 0.0, accB = 0.0;
-                    for (int kc = 0; kc < pe64; kc += 512) {
-                        double2 xa[8], xb[8];
+            // ---- phase 3: Wv = Binv v.  This CTA streams the prefixes of its rows (q % R == cr) in panels of 512
+            // columns: row-dot part into ydot[q], column (axpy) part into per-lane accumulators, reduced over the
+            // warps through shared memory; the CTA's partial vector goes to every CTA of the cluster.
+            if (p.move != MOVE_PRUNE) {
+                const int npanel = (pe16 + 511) / 512;
+                for (int pc = 0; pc < npanel; ++pc) {
+                    const int c0 = pc * 512, c1 = min(pe16, c0 + 512);
+                    const int qfirst = c0 + ((cr - c0 % R) + R) % R;
+                    const int nrows = (qfirst < pe16) ? (pe16 - 1 - qfirst) / R + 1 : 0;
+                    double yacc[16];
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const int k = kc + j * 64 + lane * 2;
-                            if (k < pe64) { xa[j] = ldcg2(rowA + k); xb[j] = ldcg2(rowB + k); }
-                        }
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const int k = kc + j * 64 + lane * 2;
-                            if (k < pe64) {
-                                const double2 vv = *reinterpret_cast<const double2*>(vd + k);
-                                accA = fma(xa[j].x, vv.x, accA); accA = fma(xa[j].y, vv.y, accA);
-                                accB = fma(xb[j].x, vv.x, accB); accB = fma(xb[j].y, vv.y, accB);
+                    for (int j = 0; j < 16; ++j) yacc[j] = 0.0;
+                    if (use_ring && wid == SW_PROD_WARP) {
+                        // npl lanes of the producer warp issue one row each per round (one thread alone caps the
+                        // issue rate).  The whole warp stays convergent: a round issues when all of its slots are
+                        // free, and npl <= nslot / 2 guarantees a round never waits on a slot it fills itself.
+                        for (int base = 0; base < nrows; base += npl) {
+                            const int i = base + lane;
+                            const bool active = lane < npl && i < nrows;
+                            const int q = qfirst + i * R;
+                            const uint32_t use = ring_base + (uint32_t)i;
+                            const int slot = (int)(use % (uint32_t)nslot);
+                            const uint32_t par = (use / (uint32_t)nslot) & 1u;
+                            bool ready = !active;
+                            while (!__all_sync(0xffffffffu, ready))
+                                if (!ready) ready = mbar_try_wait(empty_bar + slot, par ^ 1u);
+                            if (active) {
+                                const uint32_t bytes = (uint32_t)(((min(q + 1, c1) - c0) + 1) & ~1) * 8u;
+                                mbar_expect_tx(full_bar + slot, bytes);
+                                bulk_g2s(ring + (size_t)slot * slot_bytes, cv.Binv + (size_t)q * P + c0, bytes, full_bar + slot);
                             }
                         }
-                    }
-                    accA = warp_sum(accA);
-                    accB = warp_sum(accB);
-                    if (lane == 0) {
+                    } else if (wid < SW_NCW) {
+                        for (int i = wid; i < nrows; i += SW_NCW) {
+                            const int q = qfirst + i * R;
+                            const double* row;
+                            int slot = 0;
+                            if (use_ring) {
+                                const uint32_t use = ring_base + (uint32_t)i;
+                                slot = (int)(use % (uint32_t)nslot);
+                                mbar_wait(full_bar + slot, (use / (uint32_t)nslot) & 1u);
+                                row = reinterpret_cast<const double*>(ring + (size_t)slot * slot_bytes);
+                            } else {
+                                row = cv.Binv + (size_t)q * P + c0;
+                            }
+                            const double vq = vd[q];
+                            double dot = 0.0;
 #pragma unroll
-                        for (int r = 0; r < SW_MAX_R; ++r)
-                            if (r < R) { Wv_peer[r][q] = accA; Wv_peer[r][q + 1] = accB; }
+                            for (int j = 0; j < 8; ++j) {
+                                const int kk = lane * 2 + 64 * j, k = c0 + kk;
+                                if (k <= q && k < c1) {
+                                    const double2 x = use_ring ? *reinterpret_cast<const double2*>(row + kk) : ldcg2(row + kk);
+                                    dot = fma(x.x, vd[k], dot);
+                                    if (k < q) yacc[2 * j] = fma(x.x, vq, yacc[2 * j]);
+                                    if (k + 1 <= q && k + 1 < c1) {
+                                        dot = fma(x.y, vd[k + 1], dot);
+                                        if (k + 1 < q) yacc[2 * j + 1] = fma(x.y, vq, yacc[2 * j + 1]);
+                                    }
+                                }
+                            }
+                            dot = warp_sum(dot);  // every lane's slot reads are complete here
+                            if (lane == 0) {
+                                if (use_ring) mbar_arrive(empty_bar + slot);
+                                ydot[q] += dot;
+                            }
+                        }
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            *reinterpret_cast<double2*>(ypart + (size_t)wid * 512 + lane * 2 + 64 * j) =
+                                make_double2(yacc[2 * j], yacc[2 * j + 1]);
                     }
+                    if (use_ring) ring_base += (uint32_t)nrows;
+                    __syncthreads();
+                    for (int kk = tid; kk < c1 - c0; kk += SW_THREADS) {
+                        double sacc = 0.0;
+#pragma unroll
+                        for (int w = 0; w < SW_NCW; ++w) sacc += ypart[(size_t)w * 512 + kk];
+                        Wv[c0 + kk] = sacc;  // column part of this CTA (Wv doubles as scratch until the cluster sum)
+                    }
+                    __syncthreads();
+                }
+                for (int k = tid; k < pe16; k += SW_THREADS) {
+                    const double mine = Wv[k] + ydot[k];
+#pragma unroll
+                    for (int r = 0; r < SW_MAX_R; ++r)
+                        if (r < R) parts_peer[r][k] = mine;
                 }
             }
             PHASE_MARK(5);
-            cluster.sync();  // (2) all rows of Wv present everywhere
+            cluster.sync();  // (2) every CTA's partial vector present everywhere
+            if (p.move != MOVE_PRUNE) {
+                for (int k = tid; k < pe16; k += SW_THREADS) {
+                    double sacc = parts[k];
+                    if (R > 1) sacc += parts[parts_stride + k];
+                    Wv[k] = sacc;
+                }
+                __syncthreads();
+            }
             PHASE_MARK(6);
 
             // ---- phase 4: 2x2 capacitance matrix and the proposed log-MLL (identical on every CTA)
             double pvv = 0.0, pvw = 0.0;
-            for (int k = tid; k < pe64; k += SW_THREADS) {
+            for (int k = tid; k < pe16; k += SW_THREADS) {
                 pvv = fma(vd[k], Wv[k], pvv);
-                pvw = fma(vd[k], __ldcg(cv.w + k), pvw);
+                pvw = fma(vd[k], w_s[k], pvw);
             }
-            const double vWv = block_sum(pvv, red);
-            const double vw = block_sum(pvw, red);
+            block_sum2(pvv, pvw, red);
+            const double vWv = pvv, vw = pvw;
             const double dWd = Wd[a] - Wd[b];
             const double dWv = Wv[a] - Wv[b];
-            const double dw = __ldcg(cv.w + a) - __ldcg(cv.w + b);
+            const double dw = w_s[a] - w_s[b];
             M00 = dWd;
             M01 = 1.0 + dWv;
             M11 = -n_u + vWv;
@@ -310,49 +501,94 @@ sweep_trees_kernel(WsLayout lay, void* ws, bark_nodes_soa forest, bark_params pr
                 if (p.valid) {
                     ++n_valid;
                     ++n_valid_move[p.move];
-                    const unsigned long long ext = (unsigned long long)pe64;
+                    const unsigned long long ext = (unsigned long long)pe16;
                     if (p.move != MOVE_PRUNE) blk_eval += ext * ext;
                     if (accept) blk_upd += ext * ext;
-                    cols_scanned += (unsigned long long)pe64;
+                    cols_scanned += ext;
                 }
             }
         }
-
         PHASE_MARK(7);
+
         if (accept) {
-            __syncthreads();  // every thread of this CTA has finished reading w / Binv for the evaluation
+            __syncthreads();  // every thread of this CTA has finished reading w_s / Wd / Wv for the evaluation
             const int a = p.a, b = p.b;
             // M^-1 = [[al, be],[be, ga]]
             const double al = M11 / det, be = -M01 / det, ga = M00 / det;
             const double cw_d = al * Ur0 + be * Ur1, cw_v = be * Ur0 + ga * Ur1;
-            // w' = (w + eta Wd) - Wd cw_d - Wv cw_v           (this CTA's rows)
-            for (int k = r0 + tid; k < r1; k += SW_THREADS)
-                __stcg(cv.w + k, __ldcg(cv.w + k) + eta * Wd[k] - Wd[k] * cw_d - Wv[k] * cw_v);
-            // Binv' = Binv - [Wd Wv] M^-1 [Wd Wv]^T              (this CTA's rows; two rows per warp pass)
-            for (int q = r0 + 2 * wid; q < r1; q += 2 * nw) {
-                double* rowA = cv.Binv + (size_t)q * P;
-                double* rowB = rowA + P;
-                const double ad = al * Wd[q] + be * Wv[q], av = be * Wd[q] + ga * Wv[q];
-                const double bd = al * Wd[q + 1] + be * Wv[q + 1], bv = be * Wd[q + 1] + ga * Wv[q + 1];
-                for (int kc = 0; kc < pe64; kc += 512) {
-                    double2 xa[8], xb[8];
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const int k = kc + j * 64 + lane * 2;
-                        if (k < pe64) { xa[j] = ldcg2(rowA + k); xb[j] = ldcg2(rowB + k); }
-                    }
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const int k = kc + j * 64 + lane * 2;
-                        if (k < pe64) {
-                            const double2 dd = *reinterpret_cast<const double2*>(Wd + k);
-                            const double2 vv = *reinterpret_cast<const double2*>(Wv + k);
-                            xa[j].x -= ad * dd.x + av * vv.x; xa[j].y -= ad * dd.y + av * vv.y;
-                            xb[j].x -= bd * dd.x + bv * vv.x; xb[j].y -= bd * dd.y + bv * vv.y;
-                            __stcg(reinterpret_cast<double2*>(rowA + k), xa[j]);
-                            __stcg(reinterpret_cast<double2*>(rowB + k), xb[j]);
+            // w' = (w + eta Wd) - Wd cw_d - Wv cw_v           (full copy, identical on every CTA)
+            for (int k = tid; k < pe16; k += SW_THREADS) w_s[k] = w_s[k] + eta * Wd[k] - Wd[k] * cw_d - Wv[k] * cw_v;
+            // Binv' = Binv - [Wd Wv] M^-1 [Wd Wv]^T on the lower triangle: prefixes of this CTA's rows
+            {
+                const int npanel = (pe16 + 511) / 512;
+                for (int pc = 0; pc < npanel; ++pc) {
+                    const int c0 = pc * 512, c1 = min(pe16, c0 + 512);
+                    const int qfirst = c0 + ((cr - c0 % R) + R) % R;
+                    const int nrows = (qfirst < pe16) ? (pe16 - 1 - qfirst) / R + 1 : 0;
+                    if (use_ring && wid == SW_PROD_WARP) {
+                        // npl lanes of the producer warp issue one row each per round (one thread alone caps the
+                        // issue rate).  The whole warp stays convergent: a round issues when all of its slots are
+                        // free, and npl <= nslot / 2 guarantees a round never waits on a slot it fills itself.
+                        for (int base = 0; base < nrows; base += npl) {
+                            const int i = base + lane;
+                            const bool active = lane < npl && i < nrows;
+                            const int q = qfirst + i * R;
+                            const uint32_t use = ring_base + (uint32_t)i;
+                            const int slot = (int)(use % (uint32_t)nslot);
+                            const uint32_t par = (use / (uint32_t)nslot) & 1u;
+                            bool ready = !active;
+                            while (!__all_sync(0xffffffffu, ready))
+                                if (!ready) ready = mbar_try_wait(empty_bar + slot, par ^ 1u);
+                            if (active) {
+                                const uint32_t bytes = (uint32_t)(((min(q + 1, c1) - c0) + 1) & ~1) * 8u;
+                                mbar_expect_tx(full_bar + slot, bytes);
+                                bulk_g2s(ring + (size_t)slot * slot_bytes, cv.Binv + (size_t)q * P + c0, bytes, full_bar + slot);
+                            }
+                        }
+                    } else if (wid < SW_NCW) {
+                        for (int i = wid; i < nrows; i += SW_NCW) {
+                            const int q = qfirst + i * R;
+                            const double ad = al * Wd[q] + be * Wv[q], av = be * Wd[q] + ga * Wv[q];
+                            const int len2 = ((min(q + 1, c1) - c0) + 1) & ~1;
+                            if (use_ring) {
+                                const uint32_t use = ring_base + (uint32_t)i;
+                                const int slot = (int)(use % (uint32_t)nslot);
+                                mbar_wait(full_bar + slot, (use / (uint32_t)nslot) & 1u);
+                                double* row = reinterpret_cast<double*>(ring + (size_t)slot * slot_bytes);
+                                for (int kk = lane * 2; kk < len2; kk += 64) {
+                                    double2 x = *reinterpret_cast<double2*>(row + kk);
+                                    const double2 dd = *reinterpret_cast<const double2*>(Wd + c0 + kk);
+                                    const double2 vv = *reinterpret_cast<const double2*>(Wv + c0 + kk);
+                                    x.x -= ad * dd.x + av * vv.x;
+                                    x.y -= ad * dd.y + av * vv.y;
+                                    *reinterpret_cast<double2*>(row + kk) = x;
+                                }
+                                fence_proxy_async();  // generic-proxy writes to the slot -> bulk store (async proxy) reads
+                                __syncwarp();
+                                if (lane == 0) {
+                                    bulk_s2g(cv.Binv + (size_t)q * P + c0, row, (uint32_t)len2 * 8u);
+                                    bulk_commit();
+                                    bulk_wait_read0();  // the slot may be refilled once the store has read it
+                                    mbar_arrive(empty_bar + slot);
+                                }
+                            } else {
+                                double* row = cv.Binv + (size_t)q * P + c0;
+                                for (int kk = lane * 2; kk < len2; kk += 64) {
+                                    double2 x = ldcg2(row + kk);
+                                    const double2 dd = *reinterpret_cast<const double2*>(Wd + c0 + kk);
+                                    const double2 vv = *reinterpret_cast<const double2*>(Wv + c0 + kk);
+                                    x.x -= ad * dd.x + av * vv.x;
+                                    x.y -= ad * dd.y + av * vv.y;
+                                    __stcg(reinterpret_cast<double2*>(row + kk), x);
+                                }
+                            }
+                        }
+                        if (use_ring && lane == 0) {
+                            bulk_wait0();  // this warp's row stores are complete
+                            fence_proxy_async();
                         }
                     }
+                    if (use_ring) ring_base += (uint32_t)nrows;
                 }
             }
             // A' = A + v d^T + d v^T + n_u d d^T   (exact integers; atomics make the cross-CTA order irrelevant)
@@ -380,7 +616,7 @@ sweep_trees_kernel(WsLayout lay, void* ws, bark_nodes_soa forest, bark_params pr
                     atomicAdd(cv.A + (size_t)b * P + a, -nuu);
                     cv.b[a] += eta;
                     cv.b[b] -= eta;
-                    // forest edit (tree_proposals.py:146-183) + column bookkeeping
+                    // forest edit (tree_proposals.py:146-183) + column bookkeeping in global memory
                     uint16_t* cm = cv.colmap + (size_t)t * L;
                     if (p.move == MOVE_GROW) {
                         const uint32_t dep = T.depth[p.node];
@@ -396,7 +632,7 @@ sweep_trees_kernel(WsLayout lay, void* ws, bark_nodes_soa forest, bark_params pr
                         cm[p.sl] = (uint16_t)b;   // left child keeps the old leaf's column
                         cm[p.sr] = (uint16_t)a;   // right child takes the new column
                         cm[p.node] = NO_COL;
-                        cv.colused[a >> 5] |= (1u << (a & 31));
+                        cv.colused[a >> 5] = colused_s[a >> 5] | (1u << (a & 31));
                     } else if (p.move == MOVE_PRUNE) {
                         forest.active[g0 + p.sl] = 0;
                         forest.active[g0 + p.sr] = 0;
@@ -404,7 +640,7 @@ sweep_trees_kernel(WsLayout lay, void* ws, bark_nodes_soa forest, bark_params pr
                         cm[p.node] = (uint16_t)a;  // merged leaf keeps the left child's column
                         cm[p.sl] = NO_COL;
                         cm[p.sr] = NO_COL;
-                        cv.colused[b >> 5] &= ~(1u << (b & 31));
+                        cv.colused[b >> 5] = colused_s[b >> 5] & ~(1u << (b & 31));
                         cv.b[b] = 0.0;
                     } else {
                         forest.feature[g0 + p.node] = (uint32_t)p.feat;
@@ -412,20 +648,29 @@ sweep_trees_kernel(WsLayout lay, void* ws, bark_nodes_soa forest, bark_params pr
                     }
                 }
             }
+            __syncthreads();  // Binv row stores of this CTA complete; colused_s / w_s readers above are done
             if (tid == 0) {
-                if (p.move == MOVE_GROW && a + 1 > ctl->p_hi) ctl->p_hi = a + 1;
+                if (p.move == MOVE_GROW) {
+                    colused_s[a >> 5] |= (1u << (a & 31));
+                    if (a + 1 > ctl->p_hi) ctl->p_hi = a + 1;
+                } else if (p.move == MOVE_PRUNE) {
+                    colused_s[b >> 5] &= ~(1u << (b & 31));
+                    w_s[b] = 0.0;
+                }
                 ctl->q = new_q; ctl->ldt = new_ldt; ctl->mll = new_mll;
                 ++n_acc;
                 ++n_acc_move[p.move];
             }
             if (p.move == MOVE_PRUNE) {
                 // column b is now an empty leaf: make its row / column of Binv exactly (1/c) e_b
-                __syncthreads();  // this CTA's rank-2 update of its rows is complete
-                for (int k = r0 + tid; k < r1; k += SW_THREADS) __stcg(cv.Binv + (size_t)k * P + b, (k == b) ? 1.0 / c : 0.0);
-                if (b >= r0 && b < r1) {
-                    for (int k = tid; k < pe64; k += SW_THREADS) __stcg(cv.Binv + (size_t)b * P + k, (k == b) ? 1.0 / c : 0.0);
-                    if (tid == 0) __stcg(cv.w + b, 0.0);
+                for (int k = tid; k < pe16; k += SW_THREADS) {
+                    if (k <= b) {
+                        if (b % R == cr) __stcg(cv.Binv + (size_t)b * P + k, (k == b) ? 1.0 / c : 0.0);  // row b prefix
+                    } else if (k % R == cr) {
+                        __stcg(cv.Binv + (size_t)k * P + b, 0.0);                                        // column b below
+                    }
                 }
+                fence_proxy_async();  // generic stores above -> later bulk loads of these rows
             }
         }
         PHASE_MARK(8);
@@ -437,20 +682,23 @@ sweep_trees_kernel(WsLayout lay, void* ws, bark_nodes_soa forest, bark_params pr
     if (tid == 0 && cr == 0)
         for (int i = 0; i < 12; ++i) sc->phase_cycles[i] += ph_acc[i];
 #endif
-    if (tid == 0 && cr == 0) {
-        sc->q = ctl->q; sc->ldt = ctl->ldt; sc->mll = ctl->mll; sc->p_hi = ctl->p_hi;
-        sc->counters[0] += (unsigned long long)m;
-        sc->counters[1] += n_valid;
-        sc->counters[2] += n_acc;
-        sc->counters[5] += n_acc_move[0];
-        sc->counters[6] += n_acc_move[1];
-        sc->counters[7] += n_acc_move[2];
-        sc->counters[8] += n_valid_move[0];
-        sc->counters[9] += n_valid_move[1];
-        sc->counters[10] += n_valid_move[2];
-        sc->counters[11] += blk_eval;      // sum over matvec evaluations of extent^2
-        sc->counters[12] += blk_upd;       // sum over accepted updates of extent^2
-        sc->counters[13] += cols_scanned;  // leaf-bitset columns scanned for v = Z^T u
+    if (cr == 0) {
+        for (int e = tid; e < P; e += SW_THREADS) cv.w[e] = w_s[e];
+        if (tid == 0) {
+            sc->q = ctl->q; sc->ldt = ctl->ldt; sc->mll = ctl->mll; sc->p_hi = ctl->p_hi;
+            sc->counters[0] += (unsigned long long)m;
+            sc->counters[1] += n_valid;
+            sc->counters[2] += n_acc;
+            sc->counters[5] += n_acc_move[0];
+            sc->counters[6] += n_acc_move[1];
+            sc->counters[7] += n_acc_move[2];
+            sc->counters[8] += n_valid_move[0];
+            sc->counters[9] += n_valid_move[1];
+            sc->counters[10] += n_valid_move[2];
+            sc->counters[11] += blk_eval;      // sum over matvec evaluations of extent^2
+            sc->counters[12] += blk_upd;       // sum over accepted updates of extent^2
+            sc->counters[13] += cols_scanned;  // leaf-bitset columns scanned for v = Z^T u
+        }
     }
 }
 

@@ -44,8 +44,9 @@ BARKTrainParamsNumba = BARKTrainParams  # the reference's name
 
 
 def default_p_cap(m: int, node_limit: int) -> int:
-    """Leaf-column capacity: 8 leaves per tree on average (posterior forests have 1.4-2.7), multiple of 64."""
-    cap = min(m * ((node_limit + 1) // 2), max(8 * m, 128))
+    """Leaf-column capacity: 4 leaves per tree on average (posterior forests have 1.4-2.7), multiple of 64.
+    `run_bark_sampler` doubles it and re-runs (same seed, same trajectory) if a chain ever needs more."""
+    cap = min(m * ((node_limit + 1) // 2), max(4 * m, 128))
     return min(8192, ((cap + 63) // 64) * 64)
 
 
@@ -136,8 +137,31 @@ class ChainState:
                     bits=bits.cpu().numpy().view(np.uint32))
 
 
+class _ColumnOverflow(Exception):
+    pass
+
+
 def run_bark_sampler(model, data, domain, params: BARKTrainParams, *, seed=None, p_cap=None, tape=None,
                      return_trace=False, chain_offset=0, device=None, return_info=False):
+    """See `_run_bark_sampler_once`; on leaf-column overflow the run is repeated with twice the capacity
+    (deterministic: same seed / tape -> same trajectory)."""
+    if seed is None:
+        seed = int(np.random.SeedSequence().generate_state(2, dtype=np.uint32).astype(np.uint64) @ np.array([1, 2**32], dtype=np.uint64))
+    forest = model[0]
+    cap = int(p_cap) if p_cap else default_p_cap(forest.shape[1], forest.shape[2])
+    while True:
+        try:
+            return _run_bark_sampler_once(model, data, domain, params, seed=seed, p_cap=cap, tape=tape,
+                                          return_trace=return_trace, chain_offset=chain_offset, device=device,
+                                          return_info=return_info)
+        except _ColumnOverflow:
+            if cap >= 8192:
+                raise _lib.BarkError("leaf-column capacity exceeded at p_cap=8192")
+            cap = min(8192, cap * 2)
+
+
+def _run_bark_sampler_once(model, data, domain, params: BARKTrainParams, *, seed=None, p_cap=None, tape=None,
+                           return_trace=False, chain_offset=0, device=None, return_info=False):
     """Generate samples from the BARK posterior (src/bark/fitting/bark_sampler.py:95-117).
 
     model  = (forest (C,m,L) NODE_RECORD_DTYPE, noise (C,), scale (C,))
@@ -196,7 +220,10 @@ def run_bark_sampler(model, data, domain, params: BARKTrainParams, *, seed=None,
         noise_s[:, k] = r["noise"]
         scale_s[:, k] = r["scale"]
     final = st.read()
-    raise_for_status(final["status"].cpu().numpy())
+    status_host = final["status"].cpu().numpy()
+    if int(np.bitwise_or.reduce(status_host.astype(np.int64))) & _lib.ST_COL_OVERFLOW:
+        raise _ColumnOverflow()
+    raise_for_status(status_host)
     node_samples = samples.cpu().numpy().view(NODE_RECORD_DTYPE).reshape(chains, S, m, L)
     out = [node_samples, noise_s.cpu().numpy(), scale_s.cpu().numpy()]
     if return_trace:

@@ -80,7 +80,7 @@ def test_empty_forest_and_params():
     assert (p.warmup_steps, p.num_samples, p.steps_per_sample, p.num_chains) == (50, 5, 10, 1)
     c = p.to_c()
     assert list(c.proposal_weights) == [0.25, 0.25, 0.5] and c.use_softplus_transform == 1 and c.sample_scale == 0
-    assert sampler.default_p_cap(200, 100) == 1600 and sampler.default_p_cap(50, 100) == 448
+    assert sampler.default_p_cap(200, 100) == 832 and sampler.default_p_cap(50, 100) == 256
     assert sampler.default_p_cap(2, 100) % 64 == 0
 
 
