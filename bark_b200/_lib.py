@@ -40,7 +40,9 @@ SIGNATURES = {
     "bark_nodes_pack": (c_int, [NodesSoA, c_int64, c_void_p, c_void_p]),
     "bark_traverse": (c_int, [NodesSoA, c_int64, c_int64, c_int64, c_void_p, c_int64, c_int64, c_void_p, c_void_p,
                               c_void_p]),
-    "bark_gram_counts": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p, c_void_p]),
+    "bark_gram_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64, c_int64, c_int32]),
+    "bark_gram_umma": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int32, c_void_p, c_void_p,
+                               c_void_p, c_void_p, c_double, c_int, c_void_p, c_void_p, c_void_p]),
     "bark_gram_to_kernel": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_double, c_int,
                                     c_void_p, c_void_p]),
     "bark_mll_workspace_bytes": (c_size_t, [c_int64, c_int64]),

@@ -143,14 +143,37 @@ def get_leaf_vectors(nodes: np.ndarray, X: np.ndarray, feat_types: np.ndarray) -
     return (ids[:, None] == present[None, :]).to(torch.float64).cpu().numpy()
 
 
-def gram_counts_device(leaves_a, leaves_b):
+def gram_counts_device(leaves_a, leaves_b, slots=None):
     """Exact int32 co-occurrence counts (batch, Na, Nb) from leaf ids (batch, Na, m), (batch, Nb, m)."""
+    return gram_umma_device(leaves_a, leaves_b, slots=slots)[0]
+
+
+def forest_slots(nodes: np.ndarray) -> int:
+    """Upper bound on (leaf slot id + 1) over a batch of forests: highest active slot + 1."""
+    act = np.flatnonzero(nodes["active"].reshape(-1, nodes.shape[-1]).any(axis=0))
+    return int(act.max()) + 1 if act.size else 1
+
+
+def gram_umma_device(leaves_a, leaves_b, slots=None, want_counts=True, scale=None, noise=None, jitter=1e-6):
+    """Tensor-core Gram (int8 one-hot tcgen05 GEMM): returns (counts int32 or None, K f64 or None).
+    K is produced when `scale` is given; the diagonal (jitter + noise) is added when `noise` is given."""
     torch = _lib.require_cuda()
+    lib = _lib.load()
     b, na, m = leaves_a.shape
     nb = leaves_b.shape[1]
-    out = torch.empty((b, na, nb), dtype=torch.int32, device=leaves_a.device)
-    _lib.check(_lib.load().bark_gram_counts(_ptr(leaves_a), _ptr(leaves_b), b, na, nb, m, _ptr(out), _stream()))
-    return out
+    if slots is None:  # ids must be < slots: one small device reduction + host read
+        slots = int(max(int(leaves_a.max().item()), int(leaves_b.max().item())) + 1) if leaves_a.numel() else 1
+    dev = leaves_a.device
+    counts = torch.empty((b, na, nb), dtype=torch.int32, device=dev) if want_counts else None
+    K = torch.empty((b, na, nb), dtype=torch.float64, device=dev) if scale is not None else None
+    status = torch.zeros(1, dtype=torch.int32, device=dev)
+    nbytes = int(lib.bark_gram_workspace_bytes(b, na, nb, m, slots))
+    ws = torch.empty(max(nbytes, 8), dtype=torch.uint8, device=dev)
+    _lib.check(lib.bark_gram_umma(_ptr(leaves_a), _ptr(leaves_b), b, na, nb, m, slots, _ptr(counts), _ptr(K), _ptr(scale),
+                                  _ptr(noise), float(jitter), int(noise is not None), _ptr(status), _ptr(ws), _stream()))
+    if int(status.item()) & 1:
+        raise _lib.BarkError("leaf id >= slots in bark_gram_umma")
+    return counts, K
 
 
 def gram_to_kernel_device(counts, m, scale, noise=None, jitter=1e-6):
@@ -172,7 +195,7 @@ def forest_gram_counts(nodes: np.ndarray, x1: np.ndarray, x2: np.ndarray, feat_t
     ft = _feat_types_device(feat_types, dev)
     la = traverse_device(df, _as_device_f64(x1, dev), ft)
     lb = la if x2 is x1 else traverse_device(df, _as_device_f64(x2, dev), ft)
-    cnt = gram_counts_device(la, lb).cpu().numpy()
+    cnt = gram_counts_device(la, lb, slots=forest_slots(nodes)).cpu().numpy()
     return cnt.reshape(*nodes.shape[:-2], x1.shape[0], x2.shape[0])
 
 
@@ -190,9 +213,9 @@ def batched_forest_gram_matrix(nodes: np.ndarray, x1: np.ndarray, x2: np.ndarray
     ft = _feat_types_device(feat_types, dev)
     la = traverse_device(df, _as_device_f64(x1, dev), ft)
     lb = la if x2 is x1 else traverse_device(df, _as_device_f64(x2, dev), ft)
-    cnt = gram_counts_device(la, lb)
-    ones = torch.ones(cnt.shape[0], dtype=torch.float64, device=dev)
-    return gram_to_kernel_device(cnt, m, ones).cpu().numpy()
+    ones = torch.ones(la.shape[0], dtype=torch.float64, device=dev)
+    _, K0 = gram_umma_device(la, lb, slots=forest_slots(nodes), want_counts=False, scale=ones)  # fused FP64 epilogue
+    return K0.cpu().numpy()
 
 
 def batched_forest_gram_matrix_no_null(nodes: np.ndarray, x1, x2, feat_types) -> np.ndarray:

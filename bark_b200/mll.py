@@ -9,8 +9,8 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from .forest import (DeviceForest, _as_device_f64, _feat_types_device, _ptr, _stream, gram_counts_device,
-                     gram_to_kernel_device, traverse_device)
+from .forest import (DeviceForest, _as_device_f64, _feat_types_device, _ptr, _stream, forest_slots, gram_umma_device,
+                     traverse_device)
 
 
 def mll_batched_device(K, y):
@@ -28,16 +28,15 @@ def mll_batched_device(K, y):
 
 def forest_mll(nodes: np.ndarray, noise, scale, X: np.ndarray, y: np.ndarray, feat_types) -> np.ndarray:
     """Full log-MLL of a batch of forests (B, m, L) with hyper-parameters noise/scale (B,):
-    traverse -> integer Gram -> K = scale*K0 + (1e-6+noise) I -> batched Cholesky-type factorisation."""
+    traverse -> int8 tcgen05 Gram with fused FP64 epilogue K = scale*K0 + (1e-6+noise) I -> batched block LDL^T."""
     torch = _lib.require_cuda()
     dev = torch.device("cuda")
     nodes = nodes.reshape(-1, *nodes.shape[-2:])
     df = DeviceForest.from_numpy(nodes, dev)
     Xd = _as_device_f64(X, dev)
     leaves = traverse_device(df, Xd, _feat_types_device(feat_types, dev))
-    cnt = gram_counts_device(leaves, leaves)
-    K = gram_to_kernel_device(cnt, nodes.shape[-2], _as_device_f64(np.reshape(scale, -1), dev),
-                              _as_device_f64(np.reshape(noise, -1), dev))
+    _, K = gram_umma_device(leaves, leaves, slots=forest_slots(nodes), want_counts=False,
+                            scale=_as_device_f64(np.reshape(scale, -1), dev), noise=_as_device_f64(np.reshape(noise, -1), dev))
     val, _, _, status = mll_batched_device(K, _as_device_f64(np.reshape(y, -1), dev))
     if int(status.max().item()) & _lib.ST_NOT_SPD:
         raise np.linalg.LinAlgError("kernel matrix is not positive definite")

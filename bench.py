@@ -313,7 +313,7 @@ def run_b200_arm(a, rank, local_rank, world):
                        "parallelism": f"chains sharded x{world}, no data-path collective"},
             "acceptance": {"tree_accept_rate": float(dc[2] / max(dc[0], 1)), "tree_valid_rate": float(dc[1] / max(dc[0], 1)),
                            "hyper_accept_rate": float(dc[4] / max(dc[3], 1))},
-            "clocks": clk, "e2e": e2e, "gpu_launches": 2 * a.steps,
+            "clocks": clk, "e2e": e2e, "gpu_launches": 3 * a.steps,
             "roofline": roofline, "cpu_baseline": cpu_baseline,
         }
         print(json.dumps(line), flush=True)

@@ -87,9 +87,16 @@ int bark_traverse(bark_nodes_soa nodes, int64_t n_forests, int64_t m, int64_t no
                   int64_t n_points, int64_t d, const int32_t* feat_types, uint32_t* leaves, void* stream);
 
 /* ---- a4: Gram (forest_gram_matrix & batched, src/bark/forest.py:78-98) --------------------- */
-/* counts[b,i,j] = #{t: leaves_a[b,i,t] == leaves_b[b,j,t]}  (exact int32). */
-int bark_gram_counts(const uint32_t* leaves_a, const uint32_t* leaves_b, int64_t batch, int64_t na, int64_t nb,
-                     int64_t m, int32_t* counts, void* stream);
+/* counts[b,i,j] = #{t: leaves_a[b,i,t] == leaves_b[b,j,t]}  (exact int32), computed as an int8 one-hot GEMM on
+ * tcgen05 (UMMA kind::i8, s32 TMEM accumulators, operands streamed by the bulk-copy engine); the FP64 kernel matrix
+ * can be produced in the same pass.
+ * slots: upper bound on (leaf slot id + 1), i.e. ids must be < slots (<= 256); *status |= 1 otherwise.
+ * counts (batch,na,nb) i32 and K (batch,na,nb) f64 are both optional (not both NULL).  K uses scale/noise/jitter/
+ * add_diag exactly as bark_gram_to_kernel.  workspace: bark_gram_workspace_bytes(...) bytes. */
+size_t bark_gram_workspace_bytes(int64_t batch, int64_t na, int64_t nb, int64_t m, int32_t slots);
+int bark_gram_umma(const uint32_t* leaves_a, const uint32_t* leaves_b, int64_t batch, int64_t na, int64_t nb, int64_t m,
+                   int32_t slots, int32_t* counts, double* K, const double* scale, const double* noise, double jitter,
+                   int add_diag, uint32_t* status, void* workspace, void* stream);
 /* K[b] = scale[b] * ((1.0/m) * counts[b]) + (jitter + noise[b]) * I   (same multiply order as
  * src/bark/fitting/bark_sampler.py:153-156; diag added only when add_diag != 0 and na == nb). */
 int bark_gram_to_kernel(const int32_t* counts, int64_t batch, int64_t na, int64_t nb, int64_t m, const double* scale,

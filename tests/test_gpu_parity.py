@@ -344,3 +344,32 @@ def test_synthetic_generator_matches_oracle():
         for x, y in zip(a[:4], b[:4]):
             assert np.array_equal(x, y)
     assert synthetic.TreeFunction(m=7).forest.tobytes() == O.TreeFunction(m=7).forest.tobytes()
+
+
+@pytest.mark.parametrize("n,n2,m", [(65, 1, 3), (300, 129, 51), (700, 700, 201), (128, 256, 64)])
+def test_gram_umma_tensor_core_counts(n, n2, m):
+    """int8 one-hot tcgen05 GEMM: exact counts and bit-exact FP64 kernel matrix vs the oracle."""
+    import torch
+    from bark_b200.forest import DeviceForest, _as_device_f64, _feat_types_device, gram_umma_device, traverse_device
+    fn = O.TreeFunction(dim=4, cat_dim=2, num_cat=5, m=2, function_seed=3)
+    forests = random_forests(2, m, fn.bounds, fn.feat_types, sweeps=10, seed=m)
+    rng = np.random.default_rng(m)
+    X1, X2 = fn.sample_inputs(n, rng), fn.sample_inputs(n2, rng)
+    dev = torch.device("cuda")
+    df = DeviceForest.from_numpy(forests, dev)
+    ft = _feat_types_device(fn.feat_types, dev)
+    la = traverse_device(df, _as_device_f64(X1, dev), ft)
+    lb = traverse_device(df, _as_device_f64(X2, dev), ft)
+    want = np.stack([O.forest_gram_counts(f, X1, X2, fn.feat_types) for f in forests])
+    scale = torch.tensor([0.7, 1.3], dtype=torch.float64, device=dev)
+    cnt, K = gram_umma_device(la, lb, scale=scale)
+    assert np.array_equal(cnt.cpu().numpy(), want)
+    assert np.array_equal(K.cpu().numpy(), scale.cpu().numpy()[:, None, None] * ((1 / m) * want.astype(np.float64)))
+    # square case with the noise diagonal, operands shared (Z built once)
+    noise = torch.tensor([0.1, 0.02], dtype=torch.float64, device=dev)
+    cnt2, K2 = gram_umma_device(la, la, scale=scale, noise=noise)
+    want2 = np.stack([O.forest_gram_counts(f, X1, X1, fn.feat_types) for f in forests])
+    assert np.array_equal(cnt2.cpu().numpy(), want2)
+    wantK = np.stack([scale[i].item() * ((1 / m) * want2[i].astype(np.float64)) + (1e-6 + noise[i].item()) * np.eye(n)
+                      for i in range(2)])
+    assert np.array_equal(K2.cpu().numpy(), wantK)

@@ -49,7 +49,7 @@ def test_workspace_sizes_and_argument_validation(lib):
     assert lib.bark_mcmc_workspace_bytes(ctypes.byref(bad)) == 0
     assert lib.bark_mll_workspace_bytes(16, 250) > 0
     # invalid arguments are rejected before any CUDA call
-    rc = lib.bark_gram_counts(None, None, 1, 4, 4, 3, None, None)
+    rc = lib.bark_gram_umma(None, None, 1, 4, 4, 3, 8, None, None, None, None, 1e-6, 0, None, None, None)
     assert rc == 1 and b"null" in lib.bark_last_error()
 
 
