@@ -112,34 +112,51 @@ __device__ __forceinline__ void load_pivot_block(const double* G, int64_t ld, in
 
 // Scalar symmetric sweep of s.D over all NB pivots: s.D <- -D^-1, s.piv[j] <- j-th pivot (successive
 // Schur complements; their product is det D).  Returns false (uniformly) if a pivot is not positive.
+// Register-resident: every thread owns 8 fixed entries (rows r0 + 8 i, column c) of the 64 x 64 block and only
+// the next pivot row / column travel through shared memory (double-buffered), one barrier per pivot.
 __device__ __forceinline__ bool sweep_pivot_block(Smem& s) {
     const int tid = threadIdx.x;
+    const int c = tid & (NB - 1), r0 = tid >> 6;  // THREADS / NB = 8 row phases
+    double v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = s.D[r0 + 8 * i][c];
+    // pivot row / column buffers: [2][NB] each, carved from s.As (free while the pivot block is processed)
+    double* colb = &s.As[0][0];
+    double* rowb = colb + 2 * NB;
+    if (tid < NB) {
+        colb[tid] = s.D[tid][0];
+        rowb[tid] = s.D[0][tid];
+    }
+    __syncthreads();
     bool ok = true;
     for (int j = 0; j < NB; ++j) {
-        __syncthreads();
-        const double p = s.D[j][j];
-        if (tid < NB) {
-            s.colv[tid] = s.D[tid][j];
-            s.rowv[tid] = s.D[j][tid];
-        }
+        const double* colv = colb + (j & 1) * NB;
+        const double* rowv = rowb + (j & 1) * NB;
+        double* coln = colb + ((j + 1) & 1) * NB;
+        double* rown = rowb + ((j + 1) & 1) * NB;
+        const double p = colv[j];
         if (tid == 0) s.piv[j] = p;
         if (!(p > 0.0)) ok = false;
         const double ip = 1.0 / p;
-        __syncthreads();
-        for (int e = tid; e < NB * NB; e += THREADS) {
-            const int r = e / NB, c = e % NB;
-            double v;
-            if (r == j && c == j)
-                v = -ip;
-            else if (r == j)
-                v = s.rowv[c] * ip;
+        const double rc = rowv[c] * ip;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int r = r0 + 8 * i;
+            double x;
+            if (r == j)
+                x = (c == j) ? -ip : rc;
             else if (c == j)
-                v = s.colv[r] * ip;
+                x = colv[r] * ip;
             else
-                v = s.D[r][c] - s.colv[r] * ip * s.rowv[c];
-            s.D[r][c] = v;
+                x = v[i] - colv[r] * rc;
+            v[i] = x;
+            if (c == j + 1) coln[r] = x;
+            if (r == j + 1) rown[c] = x;
         }
+        __syncthreads();
     }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s.D[r0 + 8 * i][c] = v[i];
     __syncthreads();
     return ok;
 }
