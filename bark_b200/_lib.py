@@ -30,7 +30,7 @@ class McmcDims(C.Structure):
     _fields_ = [(n, c_int64) for n in ("chains", "n", "d", "m", "node_limit", "p_cap")]
 
 
-ST_TREE_OVERFLOW, ST_HYPER_MODE, ST_COL_OVERFLOW, ST_NOT_SPD = 1, 2, 4, 8
+ST_TREE_OVERFLOW, ST_HYPER_MODE, ST_COL_OVERFLOW, ST_NOT_SPD, ST_TIMEOUT = 1, 2, 4, 8, 16
 
 # name -> (restype, argtypes); mirrors include/bark_b200.h one to one
 SIGNATURES = {

@@ -31,7 +31,7 @@ constexpr int SW_WARPS = SW_THREADS / 32;
 constexpr int SW_MAX_R = 2;
 constexpr int SW_PROD_WARP = SW_WARPS - 1;  // bulk-copy producer
 constexpr int SW_NCW = SW_WARPS - 1;        // consumer warps
-constexpr int SW_NSLOT_MAX = 64;
+constexpr int SW_NSLOT_MAX = 60;  // multiple of SW_NCW
 
 #ifdef BARK_PHASE_TIMING
 #define PHASE_MARK(i)                                        \
@@ -71,8 +71,16 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     return ok != 0;
 }
 // Warp-uniform wait: every lane of the calling warp waits on the SAME barrier (no divergence inside).
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+// Bounded: a wait that does not complete within ~2^26 probes flags BARK_ST_TIMEOUT and gives up instead of
+// hanging the GPU (results of that chain are then invalid and the host raises).
+constexpr unsigned SW_WAIT_LIMIT = 1u << 26;
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, unsigned* status) {
+    unsigned spins = 0;
     while (!mbar_try_wait(bar, parity)) {
+        if (++spins > SW_WAIT_LIMIT) {
+            atomicOr(status, BARK_ST_TIMEOUT);
+            break;
+        }
     }
 }
 __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
@@ -92,8 +100,16 @@ __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 
-struct SweepCtl {  // small shared control block (kept identical on every CTA of the cluster)
-    Prop prop;
+// Rank 0 of the cluster is the single decision maker: it generates the proposal and takes the MH decision, and
+// broadcasts both (with the update coefficients) to the other CTAs through DSMEM, so the CTAs of a cluster can
+// never disagree on control flow (a disagreement would dead-lock the cluster barriers).
+struct Decision {
+    double eta, al, be, ga, cw_d, cw_v, new_q, new_ldt, new_mll;
+    int accept, pad;
+};
+struct SweepCtl {  // small shared control block
+    Prop prop[2];  // double-buffered by tree parity: rank 0 may publish t+1 while a peer still holds t
+    Decision dec;
     double q, ldt, mll;
     int p_hi;
 };
@@ -124,7 +140,7 @@ __host__ __device__ inline SweepSmemLayout sweep_smem_layout(int L, int d, int P
     s.off_bars = o;     o += align256((size_t)SW_NSLOT_MAX * 2 * 8);
     s.off_ydot = o;     o += align256((size_t)P * 8);                    // row-dot part of the symmetric matvec
     s.off_parts = o;    o += align256((size_t)P * 8) * SW_MAX_R;         // per-CTA partial vectors (DSMEM targets)
-    s.off_ypart = o;    o += align256((size_t)SW_NCW * 512 * 8);         // per-warp column accumulators of a panel
+    s.off_ypart = o;    o += align256((size_t)SW_NCW * 256 * 8);         // per-warp column accumulators, half a panel at a time
     o = (o + 1023) & ~(size_t)1023;
     s.off_ring = o;
     s.ring_bytes = (budget > o + 1024) ? ((budget - o) & ~(size_t)1023) : 0;
@@ -156,6 +172,14 @@ sweep_trees_kernel(WsLayout lay, void* ws, bark_nodes_soa forest, bark_params pr
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     cg::cluster_group cluster = cg::this_cluster();
     const int R = (int)cluster.num_blocks(), cr = (int)cluster.block_rank();
+    auto csync = [&]() {
+        if (R > 1) {
+            cluster.sync();
+            fence_proxy_async();  // reader side: peers' generic / bulk writes before our bulk / generic reads
+        } else {
+            __syncthreads();
+        }
+    };
 
     const int P = (int)lay.P, L = (int)lay.L, m = (int)lay.m, n = (int)lay.n, wd = (int)lay.wd, npad = (int)lay.npad;
     const int d = (int)lay.d;
@@ -216,11 +240,14 @@ sweep_trees_kernel(WsLayout lay, void* ws, bark_nodes_soa forest, bark_params pr
     for (int e = tid; e < P / 32; e += SW_THREADS) colused_s[e] = __ldcg(cv.colused + e);
     for (int e = tid; e < P; e += SW_THREADS) w_s[e] = __ldcg(cv.w + e);
 
-    // ring geometry for this launch: one slot per row of Binv, sized for the extent at launch + head-room
-    const int slot_cols = min(512, min(P, ((p_hi_start + 64) + 15) & ~15));  // a slot holds one row segment
+    // ring geometry for this launch: one slot per row segment, sized for the extent at launch + a little head-room
+    // (a proposal whose segments would not fit falls back to direct loads).  A slot is always consumed by the
+    // same warp (slot = use % nslot, warp = use % SW_NCW, nslot a multiple of SW_NCW): mbarrier waits only carry
+    // one parity bit, so the successive laps of a slot must be observed in order by one waiter.
+    const int slot_cols = min(512, min(P, ((p_hi_start + 16) + 15) & ~15));
     const uint32_t slot_bytes = (uint32_t)slot_cols * 8u;
-    const int nslot = (int)min((size_t)SW_NSLOT_MAX, sl.ring_bytes / slot_bytes);
-    const bool ring_ok = nslot >= 4;
+    const int nslot = (int)(min((size_t)SW_NSLOT_MAX, sl.ring_bytes / slot_bytes) / SW_NCW) * SW_NCW;
+    const bool ring_ok = nslot >= SW_NCW;
     const int npl = max(1, min(32, nslot / 2));  // producer lanes
     if (tid == 0 && ring_ok) {
         for (int i = 0; i < nslot; ++i) { mbar_init(full_bar + i, 1); mbar_init(empty_bar + i, 1); }
@@ -244,45 +271,49 @@ sweep_trees_kernel(WsLayout lay, void* ws, bark_nodes_soa forest, bark_params pr
     for (int t = 0; t < m; ++t) {
         __syncthreads();
         PHASE_MARK(11);
-        // ---- stage the tree, its column map and the root box
-        const int64_t g0 = (chain * (int64_t)m + t) * L;
-        for (int e = tid; e < L; e += SW_THREADS) {
-            T.is_leaf[e] = __ldcg(forest.is_leaf + g0 + e);
-            T.active[e] = __ldcg(forest.active + g0 + e);
-            T.feat[e] = __ldcg(forest.feature + g0 + e);
-            T.left[e] = __ldcg(forest.left + g0 + e);
-            T.right[e] = __ldcg(forest.right + g0 + e);
-            T.parent[e] = __ldcg(forest.parent + g0 + e);
-            T.depth[e] = __ldcg(forest.depth + g0 + e);
-            T.thr[e] = __ldcg(forest.threshold + g0 + e);
-            cm_s[e] = __ldcg(cv.colmap + (size_t)t * L + e);
-        }
-        for (int e = tid; e < 2 * d; e += SW_THREADS) box[e] = sv.bounds[e];
-        __syncthreads();
-        PHASE_MARK(0);
-
-        // ---- proposal (warp 0 of every CTA; identical inputs -> identical proposal)
+        // ---- rank 0 stages the tree, its column map and the root box, and generates the proposal
         double u[6];
         if (tape) {
             for (int k = 0; k < TAPE_PER_TREE; ++k) u[k] = tape[tape_base + (size_t)t * TAPE_PER_TREE + k];
         } else {
             rng_uniforms(seed, g_chain, g_sweep, (uint32_t)t, TAPE_PER_TREE, u);
         }
-        if (wid == 0) {
-            Prop p = propose_tree_warp(T, L, box, ftc, d, cm_s, colused_s, P, prm, u, &sc->status, logtab, priortab);
-            if (lane == 0) ctl->prop = p;
+        const int64_t g0 = (chain * (int64_t)m + t) * L;
+        if (cr == 0) {
+            for (int e = tid; e < L; e += SW_THREADS) {
+                T.is_leaf[e] = __ldcg(forest.is_leaf + g0 + e);
+                T.active[e] = __ldcg(forest.active + g0 + e);
+                T.feat[e] = __ldcg(forest.feature + g0 + e);
+                T.left[e] = __ldcg(forest.left + g0 + e);
+                T.right[e] = __ldcg(forest.right + g0 + e);
+                T.parent[e] = __ldcg(forest.parent + g0 + e);
+                T.depth[e] = __ldcg(forest.depth + g0 + e);
+                T.thr[e] = __ldcg(forest.threshold + g0 + e);
+                cm_s[e] = __ldcg(cv.colmap + (size_t)t * L + e);
+            }
+            for (int e = tid; e < 2 * d; e += SW_THREADS) box[e] = sv.bounds[e];
+            __syncthreads();
+            PHASE_MARK(0);
+            if (wid == 0) {
+                Prop pp = propose_tree_warp(T, L, box, ftc, d, cm_s, colused_s, P, prm, u, &sc->status, logtab, priortab);
+                if (lane == 0) {
+#pragma unroll
+                    for (int r = 0; r < SW_MAX_R; ++r)
+                        if (r < R) *cluster.map_shared_rank(&ctl->prop[t & 1], r) = pp;
+                }
+            }
         }
-        __syncthreads();
+        csync();  // (0) proposal visible on every CTA
         PHASE_MARK(1);
-        const Prop p = ctl->prop;
+        const Prop p = ctl->prop[t & 1];
         const double cur_q = ctl->q, cur_ldt = ctl->ldt, cur_mll = ctl->mll;
         const int p_hi = ctl->p_hi;
 
         double new_q = cur_q, new_ldt = cur_ldt, new_mll = cur_mll;
-        double eta = 0.0, n_u = 0.0, M00 = 0.0, M01 = 0.0, M11 = 0.0, det = -1.0, Ur0 = 0.0, Ur1 = 0.0;
+        double eta = 0.0, n_u = 0.0, al = 0.0, be = 0.0, ga = 0.0, cw_d = 0.0, cw_v = 0.0;
         int pe16 = 0, r0 = 0, r1 = 0;
         bool accept = false;
-        const bool use_ring = ring_ok;
+        bool use_ring = false;
 
         if (p.valid) {
             const int a = p.a, b = p.b;
@@ -291,6 +322,7 @@ sweep_trees_kernel(WsLayout lay, void* ws, bark_nodes_soa forest, bark_params pr
             const int share = pe16 / R;      // multiple of 4
             r0 = cr * share;
             r1 = r0 + share;
+            use_ring = ring_ok && min(pe16, 512) <= slot_cols;
             // ---- phase 1: moved-point masks u+ / u-, eta = u^T y, n_u = u^T u
             double eta_part = 0.0, cnt_part = 0.0;
             const uint32_t* bits_a = cv.bits + (size_t)a * wd;
@@ -359,7 +391,7 @@ sweep_trees_kernel(WsLayout lay, void* ws, bark_nodes_soa forest, bark_params pr
                 ydot[k] = 0.0;
             }
             PHASE_MARK(3);
-            cluster.sync();  // (1) all columns of v present everywhere
+            csync();  // (1) all columns of v present everywhere
             PHASE_MARK(4);
 
             // ---- phase 3: Wv = Binv v.  This CTA streams the prefixes of its rows (q % R == cr) in panels of 512
@@ -386,8 +418,14 @@ sweep_trees_kernel(WsLayout lay, void* ws, bark_nodes_soa forest, bark_params pr
                             const int slot = (int)(use % (uint32_t)nslot);
                             const uint32_t par = (use / (uint32_t)nslot) & 1u;
                             bool ready = !active;
-                            while (!__all_sync(0xffffffffu, ready))
+                            unsigned spins = 0;
+                            while (!__all_sync(0xffffffffu, ready)) {
                                 if (!ready) ready = mbar_try_wait(empty_bar + slot, par ^ 1u);
+                                if (++spins > SW_WAIT_LIMIT) {
+                                    atomicOr(&sc->status, BARK_ST_TIMEOUT);
+                                    break;
+                                }
+                            }
                             if (active) {
                                 const uint32_t bytes = (uint32_t)(((min(q + 1, c1) - c0) + 1) & ~1) * 8u;
                                 mbar_expect_tx(full_bar + slot, bytes);
@@ -395,14 +433,16 @@ sweep_trees_kernel(WsLayout lay, void* ws, bark_nodes_soa forest, bark_params pr
                             }
                         }
                     } else if (wid < SW_NCW) {
-                        for (int i = wid; i < nrows; i += SW_NCW) {
+                        // row i of this pass is ring use (ring_base + i): consumed by warp (use % SW_NCW)
+                        const int ifirst = use_ring ? (int)((wid + SW_NCW - (ring_base % SW_NCW)) % SW_NCW) : wid;
+                        for (int i = ifirst; i < nrows; i += SW_NCW) {
                             const int q = qfirst + i * R;
                             const double* row;
                             int slot = 0;
                             if (use_ring) {
                                 const uint32_t use = ring_base + (uint32_t)i;
                                 slot = (int)(use % (uint32_t)nslot);
-                                mbar_wait(full_bar + slot, (use / (uint32_t)nslot) & 1u);
+                                mbar_wait(full_bar + slot, (use / (uint32_t)nslot) & 1u, &sc->status);
                                 row = reinterpret_cast<const double*>(ring + (size_t)slot * slot_bytes);
                             } else {
                                 row = cv.Binv + (size_t)q * P + c0;
@@ -428,20 +468,29 @@ sweep_trees_kernel(WsLayout lay, void* ws, bark_nodes_soa forest, bark_params pr
                                 ydot[q] += dot;
                             }
                         }
-#pragma unroll
-                        for (int j = 0; j < 8; ++j)
-                            *reinterpret_cast<double2*>(ypart + (size_t)wid * 512 + lane * 2 + 64 * j) =
-                                make_double2(yacc[2 * j], yacc[2 * j + 1]);
                     }
                     if (use_ring) ring_base += (uint32_t)nrows;
-                    __syncthreads();
-                    for (int kk = tid; kk < c1 - c0; kk += SW_THREADS) {
-                        double sacc = 0.0;
+                    // reduce the per-lane column accumulators over the consumer warps, 256 columns at a time
 #pragma unroll
-                        for (int w = 0; w < SW_NCW; ++w) sacc += ypart[(size_t)w * 512 + kk];
-                        Wv[c0 + kk] = sacc;  // column part of this CTA (Wv doubles as scratch until the cluster sum)
+                    for (int half = 0; half < 2; ++half) {
+                        if (wid < SW_NCW) {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j)
+                                *reinterpret_cast<double2*>(ypart + (size_t)wid * 256 + lane * 2 + 64 * j) =
+                                    make_double2(yacc[2 * (4 * half + j)], yacc[2 * (4 * half + j) + 1]);
+                        }
+                        __syncthreads();
+                        for (int kk = tid; kk < 256; kk += SW_THREADS) {
+                            const int k = c0 + 256 * half + kk;
+                            if (k < c1) {
+                                double sacc = 0.0;
+#pragma unroll
+                                for (int w = 0; w < SW_NCW; ++w) sacc += ypart[(size_t)w * 256 + kk];
+                                Wv[k] = sacc;  // column part of this CTA (Wv doubles as scratch until the cluster sum)
+                            }
+                        }
+                        __syncthreads();
                     }
-                    __syncthreads();
                 }
                 for (int k = tid; k < pe16; k += SW_THREADS) {
                     const double mine = Wv[k] + ydot[k];
@@ -451,7 +500,7 @@ sweep_trees_kernel(WsLayout lay, void* ws, bark_nodes_soa forest, bark_params pr
                 }
             }
             PHASE_MARK(5);
-            cluster.sync();  // (2) every CTA's partial vector present everywhere
+            csync();  // (2) every CTA's partial vector present everywhere
             if (p.move != MOVE_PRUNE) {
                 for (int k = tid; k < pe16; k += SW_THREADS) {
                     double sacc = parts[k];
@@ -462,50 +511,61 @@ sweep_trees_kernel(WsLayout lay, void* ws, bark_nodes_soa forest, bark_params pr
             }
             PHASE_MARK(6);
 
-            // ---- phase 4: 2x2 capacitance matrix and the proposed log-MLL (identical on every CTA)
-            double pvv = 0.0, pvw = 0.0;
-            for (int k = tid; k < pe16; k += SW_THREADS) {
-                pvv = fma(vd[k], Wv[k], pvv);
-                pvw = fma(vd[k], w_s[k], pvw);
+            // ---- phase 4 (rank 0): 2x2 capacitance matrix, proposed log-MLL, MH decision (bark_sampler.py:257-264)
+            if (cr == 0) {
+                double pvv = 0.0, pvw = 0.0;
+                for (int k = tid; k < pe16; k += SW_THREADS) {
+                    pvv = fma(vd[k], Wv[k], pvv);
+                    pvw = fma(vd[k], w_s[k], pvw);
+                }
+                block_sum2(pvv, pvw, red);
+                if (tid == 0) {
+                    const double vWv = pvv, vw = pvw;
+                    const double dWd = Wd[a] - Wd[b];
+                    const double dWv = Wv[a] - Wv[b];
+                    const double dw = w_s[a] - w_s[b];
+                    const double M00 = dWd, M01 = 1.0 + dWv, M11 = -n_u + vWv;
+                    const double det = M00 * M11 - M01 * M01;              // < 0 for an SPD B'
+                    Decision dd;
+                    dd.new_ldt = cur_ldt + log(-det);
+                    const double bq = cur_q + 2.0 * eta * dw + eta * eta * dWd;  // b'^T Binv b'
+                    const double Ur0 = dw + eta * dWd;                           // d^T r,  r = Binv b'
+                    const double Ur1 = vw + eta * dWv;                           // v^T r
+                    dd.new_q = bq - (M11 * Ur0 * Ur0 - 2.0 * M01 * Ur0 * Ur1 + M00 * Ur1 * Ur1) / det;
+                    dd.new_mll = 0.5 * (-(yy - dd.new_q) / sig - nlogsig - dd.new_ldt);
+                    const double log_alpha = p.lqp + (dd.new_mll - cur_mll);
+                    dd.accept = (log(u[4]) <= fmin(log_alpha, 0.0)) ? 1 : 0;
+                    // M^-1 = [[al, be],[be, ga]] and the coefficients of the w update
+                    dd.al = M11 / det; dd.be = -M01 / det; dd.ga = M00 / det;
+                    dd.cw_d = dd.al * Ur0 + dd.be * Ur1;
+                    dd.cw_v = dd.be * Ur0 + dd.ga * Ur1;
+                    dd.eta = eta;
+                    dd.pad = 0;
+#pragma unroll
+                    for (int r = 0; r < SW_MAX_R; ++r)
+                        if (r < R) *cluster.map_shared_rank(&ctl->dec, r) = dd;
+                }
             }
-            block_sum2(pvv, pvw, red);
-            const double vWv = pvv, vw = pvw;
-            const double dWd = Wd[a] - Wd[b];
-            const double dWv = Wv[a] - Wv[b];
-            const double dw = w_s[a] - w_s[b];
-            M00 = dWd;
-            M01 = 1.0 + dWv;
-            M11 = -n_u + vWv;
-            det = M00 * M11 - M01 * M01;                 // < 0 for an SPD B'
-            new_ldt = cur_ldt + log(-det);
-            const double bq = cur_q + 2.0 * eta * dw + eta * eta * dWd;  // b'^T Binv b'
-            Ur0 = dw + eta * dWd;                                         // d^T r,  r = Binv b'
-            Ur1 = vw + eta * dWv;                                         // v^T r
-            new_q = bq - (M11 * Ur0 * Ur0 - 2.0 * M01 * Ur0 * Ur1 + M00 * Ur1 * Ur1) / det;
-            new_mll = 0.5 * (-(yy - new_q) / sig - nlogsig - new_ldt);
+            csync();  // (2b) decision visible on every CTA
+            const Decision dec = ctl->dec;
+            accept = dec.accept != 0;
+            new_q = dec.new_q; new_ldt = dec.new_ldt; new_mll = dec.new_mll;
+            eta = dec.eta; al = dec.al; be = dec.be; ga = dec.ga; cw_d = dec.cw_d; cw_v = dec.cw_v;
         }
 
-        // ---- MH accept (bark_sampler.py:257-264); every thread of every CTA evaluates the same scalars
-        {
-            const double u_acc = u[4];
-            if (p.valid) {
-                const double log_alpha = p.lqp + (new_mll - cur_mll);
-                accept = log(u_acc) <= fmin(log_alpha, 0.0);
+        if (tid == 0) {
+            if (trace_base && cr == 0) {
+                trace_base[t * 3 + 0] = p.valid ? p.lqp : -INFINITY;
+                trace_base[t * 3 + 1] = new_mll;
+                trace_base[t * 3 + 2] = accept ? 1.0 : 0.0;
             }
-            if (tid == 0) {
-                if (trace_base && cr == 0) {
-                    trace_base[t * 3 + 0] = p.valid ? p.lqp : -INFINITY;
-                    trace_base[t * 3 + 1] = new_mll;
-                    trace_base[t * 3 + 2] = accept ? 1.0 : 0.0;
-                }
-                if (p.valid) {
-                    ++n_valid;
-                    ++n_valid_move[p.move];
-                    const unsigned long long ext = (unsigned long long)pe16;
-                    if (p.move != MOVE_PRUNE) blk_eval += ext * ext;
-                    if (accept) blk_upd += ext * ext;
-                    cols_scanned += ext;
-                }
+            if (p.valid) {
+                ++n_valid;
+                ++n_valid_move[p.move];
+                const unsigned long long ext = (unsigned long long)pe16;
+                if (p.move != MOVE_PRUNE) blk_eval += ext * ext;
+                if (accept) blk_upd += ext * ext;
+                cols_scanned += ext;
             }
         }
         PHASE_MARK(7);
@@ -513,9 +573,6 @@ sweep_trees_kernel(WsLayout lay, void* ws, bark_nodes_soa forest, bark_params pr
         if (accept) {
             __syncthreads();  // every thread of this CTA has finished reading w_s / Wd / Wv for the evaluation
             const int a = p.a, b = p.b;
-            // M^-1 = [[al, be],[be, ga]]
-            const double al = M11 / det, be = -M01 / det, ga = M00 / det;
-            const double cw_d = al * Ur0 + be * Ur1, cw_v = be * Ur0 + ga * Ur1;
             // w' = (w + eta Wd) - Wd cw_d - Wv cw_v           (full copy, identical on every CTA)
             for (int k = tid; k < pe16; k += SW_THREADS) w_s[k] = w_s[k] + eta * Wd[k] - Wd[k] * cw_d - Wv[k] * cw_v;
             // Binv' = Binv - [Wd Wv] M^-1 [Wd Wv]^T on the lower triangle: prefixes of this CTA's rows
@@ -537,8 +594,14 @@ sweep_trees_kernel(WsLayout lay, void* ws, bark_nodes_soa forest, bark_params pr
                             const int slot = (int)(use % (uint32_t)nslot);
                             const uint32_t par = (use / (uint32_t)nslot) & 1u;
                             bool ready = !active;
-                            while (!__all_sync(0xffffffffu, ready))
+                            unsigned spins = 0;
+                            while (!__all_sync(0xffffffffu, ready)) {
                                 if (!ready) ready = mbar_try_wait(empty_bar + slot, par ^ 1u);
+                                if (++spins > SW_WAIT_LIMIT) {
+                                    atomicOr(&sc->status, BARK_ST_TIMEOUT);
+                                    break;
+                                }
+                            }
                             if (active) {
                                 const uint32_t bytes = (uint32_t)(((min(q + 1, c1) - c0) + 1) & ~1) * 8u;
                                 mbar_expect_tx(full_bar + slot, bytes);
@@ -546,14 +609,15 @@ sweep_trees_kernel(WsLayout lay, void* ws, bark_nodes_soa forest, bark_params pr
                             }
                         }
                     } else if (wid < SW_NCW) {
-                        for (int i = wid; i < nrows; i += SW_NCW) {
+                        const int ifirst = use_ring ? (int)((wid + SW_NCW - (ring_base % SW_NCW)) % SW_NCW) : wid;
+                        for (int i = ifirst; i < nrows; i += SW_NCW) {
                             const int q = qfirst + i * R;
                             const double ad = al * Wd[q] + be * Wv[q], av = be * Wd[q] + ga * Wv[q];
                             const int len2 = ((min(q + 1, c1) - c0) + 1) & ~1;
                             if (use_ring) {
                                 const uint32_t use = ring_base + (uint32_t)i;
                                 const int slot = (int)(use % (uint32_t)nslot);
-                                mbar_wait(full_bar + slot, (use / (uint32_t)nslot) & 1u);
+                                mbar_wait(full_bar + slot, (use / (uint32_t)nslot) & 1u, &sc->status);
                                 double* row = reinterpret_cast<double*>(ring + (size_t)slot * slot_bytes);
                                 for (int kk = lane * 2; kk < len2; kk += 64) {
                                     double2 x = *reinterpret_cast<double2*>(row + kk);
@@ -674,7 +738,7 @@ sweep_trees_kernel(WsLayout lay, void* ws, bark_nodes_soa forest, bark_params pr
             }
         }
         PHASE_MARK(8);
-        if (p.valid) cluster.sync();  // (3) peer's global-memory edits visible; exchanged vectors free for reuse
+        if (p.valid) csync();  // (3) peer's global-memory edits visible; exchanged vectors free for reuse
     }
     PHASE_MARK(9);
     __syncthreads();

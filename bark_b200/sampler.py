@@ -58,6 +58,8 @@ def raise_for_status(status: np.ndarray):
         raise NotImplementedError("You must sample the scale parameter in the log space")  # noise_scale_proposals.py:78-81
     if bits & _lib.ST_COL_OVERFLOW:
         raise _lib.BarkError("leaf-column capacity exceeded: pass a larger p_cap to run_bark_sampler")
+    if bits & _lib.ST_TIMEOUT:
+        raise _lib.BarkError("device pipeline wait timed out (internal error)")
     if bits & _lib.ST_NOT_SPD:
         raise np.linalg.LinAlgError("B = c I + Z^T Z lost positive definiteness")
 

@@ -43,6 +43,7 @@ extern "C" {
                                     NotImplementedError, src/bark/fitting/noise_scale_proposals.py:78-81 */
 #define BARK_ST_COL_OVERFLOW 4u  /* leaf-column capacity p_cap exhausted (re-run with a larger p_cap)   */
 #define BARK_ST_NOT_SPD 8u       /* Cholesky met a non-positive pivot                                  */
+#define BARK_ST_TIMEOUT 16u      /* a device-side pipeline wait gave up (internal error; results invalid) */
 
 /* NODE_RECORD_DTYPE (src/bark/forest.py:8-19): packed 26-byte records
  * is_leaf u8@0, feature_idx u32@1, threshold f32@5, left u32@9, right u32@13,
