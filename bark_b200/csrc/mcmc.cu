@@ -224,10 +224,12 @@ chain_init_kernel(WsLayout lay, void* ws, bark_nodes_soa forest, const double* _
 //                        refreshes K^-1 at the same point, :276-282)
 // =====================================================================================================
 constexpr int HYPER_CLUSTER = 8;
+constexpr int HYPER_REFRESH_EVERY = 8;  // sweeps between forced exact refreshes (0 = only on accept; replay mode)
 
 __global__ void __launch_bounds__(la::THREADS, 1)
 hyper_eval_kernel(WsLayout lay, void* ws, bark_params prm, int64_t sweep_in_call, int64_t n_sweeps_call, uint64_t seed,
-                  int64_t chain_offset, int64_t sweep_offset, const double* __restrict__ tape, double* __restrict__ trace) {
+                  int64_t chain_offset, int64_t sweep_offset, const double* __restrict__ tape, double* __restrict__ trace,
+                  int refresh_every) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     la::Smem& s = *reinterpret_cast<la::Smem*>(smem_raw);
     __shared__ HyperProp hp;
@@ -292,6 +294,12 @@ hyper_eval_kernel(WsLayout lay, void* ws, bark_params prm, int64_t sweep_in_call
             sc->prop_scale = hp.scale;
             sc->hyper_accept = 1;
             sc->counters[4] += 1ull;
+        } else if (refresh_every > 0 && ((sweep_offset + sweep_in_call + 1) % refresh_every) == 0) {
+            // periodic exact refresh of the running state (bounds the drift of the rank-2 updates between accepted
+            // noise/scale moves; the reference only refreshes on accept, bark_sampler.py:276-282)
+            sc->prop_noise = sc->noise;
+            sc->prop_scale = sc->scale;
+            sc->hyper_accept = 2;
         }
     }
 }
@@ -417,8 +425,8 @@ static int pick_cluster_size(int64_t chains) {
 static cudaError_t launch_hyper(cudaStream_t st, const WsLayout& lay, void* ws, const bark_params& prm, int64_t sidx,
                                 int64_t n_sweeps, uint64_t seed, int64_t chain_offset, int64_t sweep_offset,
                                 const double* tape, double* trace) {
-    hyper_eval_kernel<<<(unsigned)lay.chains, la::THREADS, sizeof(la::Smem), st>>>(lay, ws, prm, sidx, n_sweeps, seed,
-                                                                               chain_offset, sweep_offset, tape, trace);
+    hyper_eval_kernel<<<(unsigned)lay.chains, la::THREADS, sizeof(la::Smem), st>>>(
+        lay, ws, prm, sidx, n_sweeps, seed, chain_offset, sweep_offset, tape, trace, tape ? 0 : HYPER_REFRESH_EVERY);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(lay.chains * HYPER_CLUSTER));
     cfg.blockDim = dim3(la::THREADS);

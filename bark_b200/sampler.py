@@ -226,7 +226,11 @@ def _run_bark_sampler_once(model, data, domain, params: BARKTrainParams, *, seed
     if int(np.bitwise_or.reduce(status_host.astype(np.int64))) & _lib.ST_COL_OVERFLOW:
         raise _ColumnOverflow()
     raise_for_status(status_host)
-    node_samples = samples.cpu().numpy().view(NODE_RECORD_DTYPE).reshape(chains, S, m, L)
+    # D2H through pinned host memory (torch's caching host allocator reuses the block across calls)
+    host = torch.empty(samples.shape, dtype=torch.uint8, pin_memory=True)
+    host.copy_(samples, non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    node_samples = host.numpy().view(NODE_RECORD_DTYPE).reshape(chains, S, m, L)
     out = [node_samples, noise_s.cpu().numpy(), scale_s.cpu().numpy()]
     if return_trace:
         out.append(torch.cat(traces, dim=1).cpu().numpy() if traces else np.zeros((chains, 0, m + 1, 3)))
