@@ -41,7 +41,7 @@ __host__ __device__ inline size_t align256(size_t x) { return (x + 255) & ~(size
 __host__ __device__ inline WsLayout make_layout(const bark_mcmc_dims& dm) {
     WsLayout w;
     w.chains = dm.chains; w.n = dm.n; w.d = dm.d; w.m = dm.m; w.L = dm.node_limit; w.P = dm.p_cap;
-    w.wd = (dm.n + 31) / 32;
+    w.wd = (((dm.n + 31) / 32) + 3) & ~(int64_t)3;  // words per leaf bitset, padded to 16 bytes (uint4 loads)
     w.npad = w.wd * 32;
     size_t o = 0;
     w.off_xt = o;     o = align256(o + (size_t)w.d * w.npad * sizeof(double));

@@ -96,6 +96,7 @@ __device__ __forceinline__ void bulk_s2g(void* gdst, const void* smem_src, uint3
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
@@ -363,13 +364,21 @@ sweep_trees_kernel(WsLayout lay, void* ws, bark_nodes_soa forest, bark_params pr
                 int cnt = 0;
                 if (q < r1 && q < pe) {
                     const uint32_t* bq = cv.bits + (size_t)q * wd;
-                    for (int w0 = part * 4; w0 < wd; w0 += 16) {
-                        uint32_t x[4];
+                    // wd is a multiple of 4: 16-byte loads, up to four in flight per thread
+                    for (int w0 = part * 4; w0 < wd; w0 += 64) {
+                        uint4 x[4];
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) x[j] = (w0 + j < wd) ? __ldcg(bq + w0 + j) : 0u;
+                        for (int g = 0; g < 4; ++g)
+                            x[g] = (w0 + 16 * g < wd) ? __ldcg(reinterpret_cast<const uint4*>(bq + w0 + 16 * g)) : make_uint4(0, 0, 0, 0);
 #pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            if (w0 + j < wd) cnt += __popc(x[j] & upos[w0 + j]) - __popc(x[j] & uneg[w0 + j]);
+                        for (int g = 0; g < 4; ++g) {
+                            if (w0 + 16 * g < wd) {
+                                const uint4 up = *reinterpret_cast<const uint4*>(upos + w0 + 16 * g);
+                                const uint4 un = *reinterpret_cast<const uint4*>(uneg + w0 + 16 * g);
+                                cnt += __popc(x[g].x & up.x) + __popc(x[g].y & up.y) + __popc(x[g].z & up.z) + __popc(x[g].w & up.w);
+                                cnt -= __popc(x[g].x & un.x) + __popc(x[g].y & un.y) + __popc(x[g].z & un.z) + __popc(x[g].w & un.w);
+                            }
+                        }
                     }
                 }
                 cnt += __shfl_xor_sync(0xffffffffu, cnt, 1);
@@ -610,6 +619,7 @@ sweep_trees_kernel(WsLayout lay, void* ws, bark_nodes_soa forest, bark_params pr
                         }
                     } else if (wid < SW_NCW) {
                         const int ifirst = use_ring ? (int)((wid + SW_NCW - (ring_base % SW_NCW)) % SW_NCW) : wid;
+                        int prev_slot = -1;
                         for (int i = ifirst; i < nrows; i += SW_NCW) {
                             const int q = qfirst + i * R;
                             const double ad = al * Wd[q] + be * Wv[q], av = be * Wd[q] + ga * Wv[q];
@@ -632,9 +642,14 @@ sweep_trees_kernel(WsLayout lay, void* ws, bark_nodes_soa forest, bark_params pr
                                 if (lane == 0) {
                                     bulk_s2g(cv.Binv + (size_t)q * P + c0, row, (uint32_t)len2 * 8u);
                                     bulk_commit();
-                                    bulk_wait_read0();  // the slot may be refilled once the store has read it
-                                    mbar_arrive(empty_bar + slot);
+                                    // release the PREVIOUS slot of this warp once its store has read shared memory
+                                    // (at most one store group stays pending, so this one overlaps the next row)
+                                    if (prev_slot >= 0) {
+                                        bulk_wait_read1();
+                                        mbar_arrive(empty_bar + prev_slot);
+                                    }
                                 }
+                                prev_slot = slot;
                             } else {
                                 double* row = cv.Binv + (size_t)q * P + c0;
                                 for (int kk = lane * 2; kk < len2; kk += 64) {
@@ -648,6 +663,10 @@ sweep_trees_kernel(WsLayout lay, void* ws, bark_nodes_soa forest, bark_params pr
                             }
                         }
                         if (use_ring && lane == 0) {
+                            if (prev_slot >= 0) {
+                                bulk_wait_read0();
+                                mbar_arrive(empty_bar + prev_slot);
+                            }
                             bulk_wait0();  // this warp's row stores are complete
                             fence_proxy_async();
                         }

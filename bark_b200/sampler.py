@@ -128,7 +128,7 @@ class ChainState:
         """Leaf-space state of one chain as numpy arrays (verification only)."""
         torch = _lib.require_cuda()
         P, dev = self.p_cap, self.device
-        wd = (self.n + 31) // 32
+        wd = (((self.n + 31) // 32) + 3) // 4 * 4  # words per leaf bitset, padded to 16 bytes
         A = torch.empty((P, P), dtype=torch.int32, device=dev)
         Binv = torch.empty((P, P), dtype=torch.float64, device=dev)
         colmap = torch.empty((self.m, self.L), dtype=torch.int32, device=dev)
