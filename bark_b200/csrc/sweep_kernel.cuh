@@ -245,7 +245,8 @@ sweep_trees_kernel(WsLayout lay, void* ws, bark_nodes_soa forest, bark_params pr
     // (a proposal whose segments would not fit falls back to direct loads).  A slot is always consumed by the
     // same warp (slot = use % nslot, warp = use % SW_NCW, nslot a multiple of SW_NCW): mbarrier waits only carry
     // one parity bit, so the successive laps of a slot must be observed in order by one waiter.
-    const int slot_cols = min(512, min(P, ((p_hi_start + 16) + 15) & ~15));
+    // (+16: a slot also takes a PAIR of complementary row prefixes, short + long, total <= extent + 4)
+    const int slot_cols = min(528, min(P, ((p_hi_start + 16) + 15) & ~15) + 16);
     const uint32_t slot_bytes = (uint32_t)slot_cols * 8u;
     const int nslot = (int)(min((size_t)SW_NSLOT_MAX, sl.ring_bytes / slot_bytes) / SW_NCW) * SW_NCW;
     const bool ring_ok = nslot >= SW_NCW;
@@ -324,6 +325,7 @@ sweep_trees_kernel(WsLayout lay, void* ws, bark_nodes_soa forest, bark_params pr
             r0 = cr * share;
             r1 = r0 + share;
             use_ring = ring_ok && min(pe16, 512) <= slot_cols;
+            const bool paired = use_ring && pe16 <= 512 && pe16 + 4 <= slot_cols;  // single panel, two rows per slot
             // ---- phase 1: moved-point masks u+ / u-, eta = u^T y, n_u = u^T u
             double eta_part = 0.0, cnt_part = 0.0;
             const uint32_t* bits_a = cv.bits + (size_t)a * wd;
@@ -406,7 +408,114 @@ sweep_trees_kernel(WsLayout lay, void* ws, bark_nodes_soa forest, bark_params pr
             // ---- phase 3: Wv = Binv v.  This CTA streams the prefixes of its rows (q % R == cr) in panels of 512
             // columns: row-dot part into ydot[q], column (axpy) part into per-lane accumulators, reduced over the
             // warps through shared memory; the CTA's partial vector goes to every CTA of the cluster.
-            if (p.move != MOVE_PRUNE) {
+            if (p.move != MOVE_PRUNE && paired) {
+                // Single panel, rows paired short + long (i-th and (nrows-1-i)-th of this CTA's rows): every slot
+                // carries ~extent doubles, so the ring holds twice the bytes in flight and half the hand-offs.
+                const int qfirst = cr;
+                const int nrows = (qfirst < pe16) ? (pe16 - 1 - qfirst) / R + 1 : 0;
+                const int npairs = (nrows + 1) / 2;
+                double yacc[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) yacc[j] = 0.0;
+                if (wid == SW_PROD_WARP) {
+                    for (int base = 0; base < npairs; base += npl) {
+                        const int j = base + lane;
+                        const bool active = lane < npl && j < npairs;
+                        const int iA = j, iB = nrows - 1 - j;
+                        const int qA = qfirst + iA * R, qB = qfirst + iB * R;
+                        const uint32_t use = ring_base + (uint32_t)j;
+                        const int slot = (int)(use % (uint32_t)nslot);
+                        const uint32_t par = (use / (uint32_t)nslot) & 1u;
+                        bool ready = !active;
+                        unsigned spins = 0;
+                        while (!__all_sync(0xffffffffu, ready)) {
+                            if (!ready) ready = mbar_try_wait(empty_bar + slot, par ^ 1u);
+                            if (++spins > SW_WAIT_LIMIT) {
+                                atomicOr(&sc->status, BARK_ST_TIMEOUT);
+                                break;
+                            }
+                        }
+                        if (active) {
+                            const int lenA = (qA + 2) & ~1, lenB = (iB > iA) ? ((qB + 2) & ~1) : 0;
+                            unsigned char* dst = ring + (size_t)slot * slot_bytes;
+                            mbar_expect_tx(full_bar + slot, (uint32_t)(lenA + lenB) * 8u);
+                            bulk_g2s(dst, cv.Binv + (size_t)qA * P, (uint32_t)lenA * 8u, full_bar + slot);
+                            if (lenB) bulk_g2s(dst + (size_t)lenA * 8, cv.Binv + (size_t)qB * P, (uint32_t)lenB * 8u, full_bar + slot);
+                        }
+                    }
+                } else {
+                    const int jfirst = (int)((wid + SW_NCW - (ring_base % SW_NCW)) % SW_NCW);
+                    for (int j = jfirst; j < npairs; j += SW_NCW) {
+                        const int iA = j, iB = nrows - 1 - j;
+                        const int qA = qfirst + iA * R, qB = qfirst + iB * R;
+                        const int lenA = (qA + 2) & ~1;
+                        const bool hasB = iB > iA;
+                        const uint32_t use = ring_base + (uint32_t)j;
+                        const int slot = (int)(use % (uint32_t)nslot);
+                        mbar_wait(full_bar + slot, (use / (uint32_t)nslot) & 1u, &sc->status);
+                        const double* rowA = reinterpret_cast<const double*>(ring + (size_t)slot * slot_bytes);
+                        const double* rowB = rowA + lenA;
+                        const double vqA = vd[qA], vqB = hasB ? vd[qB] : 0.0;
+                        double dotA = 0.0, dotB = 0.0;
+#pragma unroll
+                        for (int jj = 0; jj < 8; ++jj) {
+                            const int k = lane * 2 + 64 * jj;
+                            if (k <= qA) {
+                                const double2 x = *reinterpret_cast<const double2*>(rowA + k);
+                                dotA = fma(x.x, vd[k], dotA);
+                                if (k < qA) yacc[2 * jj] = fma(x.x, vqA, yacc[2 * jj]);
+                                if (k + 1 <= qA) {
+                                    dotA = fma(x.y, vd[k + 1], dotA);
+                                    if (k + 1 < qA) yacc[2 * jj + 1] = fma(x.y, vqA, yacc[2 * jj + 1]);
+                                }
+                            }
+                            if (hasB && k <= qB) {
+                                const double2 x = *reinterpret_cast<const double2*>(rowB + k);
+                                dotB = fma(x.x, vd[k], dotB);
+                                if (k < qB) yacc[2 * jj] = fma(x.x, vqB, yacc[2 * jj]);
+                                if (k + 1 <= qB) {
+                                    dotB = fma(x.y, vd[k + 1], dotB);
+                                    if (k + 1 < qB) yacc[2 * jj + 1] = fma(x.y, vqB, yacc[2 * jj + 1]);
+                                }
+                            }
+                        }
+                        dotA = warp_sum(dotA);  // every lane's slot reads are complete here
+                        dotB = warp_sum(dotB);
+                        if (lane == 0) {
+                            mbar_arrive(empty_bar + slot);
+                            ydot[qA] += dotA;
+                            if (hasB) ydot[qB] += dotB;
+                        }
+                    }
+                }
+                ring_base += (uint32_t)npairs;
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    if (wid < SW_NCW) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            *reinterpret_cast<double2*>(ypart + (size_t)wid * 256 + lane * 2 + 64 * j) =
+                                make_double2(yacc[2 * (4 * half + j)], yacc[2 * (4 * half + j) + 1]);
+                    }
+                    __syncthreads();
+                    for (int kk = tid; kk < 256; kk += SW_THREADS) {
+                        const int k = 256 * half + kk;
+                        if (k < pe16) {
+                            double sacc = 0.0;
+#pragma unroll
+                            for (int w = 0; w < SW_NCW; ++w) sacc += ypart[(size_t)w * 256 + kk];
+                            Wv[k] = sacc;
+                        }
+                    }
+                    __syncthreads();
+                }
+                for (int k = tid; k < pe16; k += SW_THREADS) {
+                    const double mine = Wv[k] + ydot[k];
+#pragma unroll
+                    for (int r = 0; r < SW_MAX_R; ++r)
+                        if (r < R) parts_peer[r][k] = mine;
+                }
+            } else if (p.move != MOVE_PRUNE) {
                 const int npanel = (pe16 + 511) / 512;
                 for (int pc = 0; pc < npanel; ++pc) {
                     const int c0 = pc * 512, c1 = min(pe16, c0 + 512);
@@ -585,7 +694,93 @@ sweep_trees_kernel(WsLayout lay, void* ws, bark_nodes_soa forest, bark_params pr
             // w' = (w + eta Wd) - Wd cw_d - Wv cw_v           (full copy, identical on every CTA)
             for (int k = tid; k < pe16; k += SW_THREADS) w_s[k] = w_s[k] + eta * Wd[k] - Wd[k] * cw_d - Wv[k] * cw_v;
             // Binv' = Binv - [Wd Wv] M^-1 [Wd Wv]^T on the lower triangle: prefixes of this CTA's rows
-            {
+            const bool paired_u = use_ring && pe16 <= 512 && pe16 + 4 <= slot_cols;
+            if (paired_u) {
+                const int qfirst = cr;
+                const int nrows = (qfirst < pe16) ? (pe16 - 1 - qfirst) / R + 1 : 0;
+                const int npairs = (nrows + 1) / 2;
+                if (wid == SW_PROD_WARP) {
+                    for (int base = 0; base < npairs; base += npl) {
+                        const int j = base + lane;
+                        const bool active = lane < npl && j < npairs;
+                        const int iA = j, iB = nrows - 1 - j;
+                        const int qA = qfirst + iA * R, qB = qfirst + iB * R;
+                        const uint32_t use = ring_base + (uint32_t)j;
+                        const int slot = (int)(use % (uint32_t)nslot);
+                        const uint32_t par = (use / (uint32_t)nslot) & 1u;
+                        bool ready = !active;
+                        unsigned spins = 0;
+                        while (!__all_sync(0xffffffffu, ready)) {
+                            if (!ready) ready = mbar_try_wait(empty_bar + slot, par ^ 1u);
+                            if (++spins > SW_WAIT_LIMIT) {
+                                atomicOr(&sc->status, BARK_ST_TIMEOUT);
+                                break;
+                            }
+                        }
+                        if (active) {
+                            const int lenA = (qA + 2) & ~1, lenB = (iB > iA) ? ((qB + 2) & ~1) : 0;
+                            unsigned char* dst = ring + (size_t)slot * slot_bytes;
+                            mbar_expect_tx(full_bar + slot, (uint32_t)(lenA + lenB) * 8u);
+                            bulk_g2s(dst, cv.Binv + (size_t)qA * P, (uint32_t)lenA * 8u, full_bar + slot);
+                            if (lenB) bulk_g2s(dst + (size_t)lenA * 8, cv.Binv + (size_t)qB * P, (uint32_t)lenB * 8u, full_bar + slot);
+                        }
+                    }
+                } else {
+                    const int jfirst = (int)((wid + SW_NCW - (ring_base % SW_NCW)) % SW_NCW);
+                    int prev_slot = -1;
+                    for (int j = jfirst; j < npairs; j += SW_NCW) {
+                        const int iA = j, iB = nrows - 1 - j;
+                        const int qA = qfirst + iA * R, qB = qfirst + iB * R;
+                        const int lenA = (qA + 2) & ~1;
+                        const bool hasB = iB > iA;
+                        const int lenB = hasB ? ((qB + 2) & ~1) : 0;
+                        const double adA = al * Wd[qA] + be * Wv[qA], avA = be * Wd[qA] + ga * Wv[qA];
+                        const double adB = hasB ? al * Wd[qB] + be * Wv[qB] : 0.0, avB = hasB ? be * Wd[qB] + ga * Wv[qB] : 0.0;
+                        const uint32_t use = ring_base + (uint32_t)j;
+                        const int slot = (int)(use % (uint32_t)nslot);
+                        mbar_wait(full_bar + slot, (use / (uint32_t)nslot) & 1u, &sc->status);
+                        double* rowA = reinterpret_cast<double*>(ring + (size_t)slot * slot_bytes);
+                        double* rowB = rowA + lenA;
+                        for (int kk = lane * 2; kk < lenB || kk < lenA; kk += 64) {
+                            const double2 dd = *reinterpret_cast<const double2*>(Wd + kk);
+                            const double2 vv = *reinterpret_cast<const double2*>(Wv + kk);
+                            if (kk < lenA) {
+                                double2 x = *reinterpret_cast<double2*>(rowA + kk);
+                                x.x -= adA * dd.x + avA * vv.x;
+                                x.y -= adA * dd.y + avA * vv.y;
+                                *reinterpret_cast<double2*>(rowA + kk) = x;
+                            }
+                            if (kk < lenB) {
+                                double2 x = *reinterpret_cast<double2*>(rowB + kk);
+                                x.x -= adB * dd.x + avB * vv.x;
+                                x.y -= adB * dd.y + avB * vv.y;
+                                *reinterpret_cast<double2*>(rowB + kk) = x;
+                            }
+                        }
+                        fence_proxy_async();  // generic-proxy writes to the slot -> bulk store (async proxy) reads
+                        __syncwarp();
+                        if (lane == 0) {
+                            bulk_s2g(cv.Binv + (size_t)qA * P, rowA, (uint32_t)lenA * 8u);
+                            if (hasB) bulk_s2g(cv.Binv + (size_t)qB * P, rowB, (uint32_t)lenB * 8u);
+                            bulk_commit();
+                            if (prev_slot >= 0) {
+                                bulk_wait_read1();
+                                mbar_arrive(empty_bar + prev_slot);
+                            }
+                        }
+                        prev_slot = slot;
+                    }
+                    if (lane == 0) {
+                        if (prev_slot >= 0) {
+                            bulk_wait_read0();
+                            mbar_arrive(empty_bar + prev_slot);
+                        }
+                        bulk_wait0();  // this warp's row stores are complete
+                        fence_proxy_async();
+                    }
+                }
+                ring_base += (uint32_t)npairs;
+            } else {
                 const int npanel = (pe16 + 511) / 512;
                 for (int pc = 0; pc < npanel; ++pc) {
                     const int c0 = pc * 512, c1 = min(pe16, c0 + 512);
