@@ -26,6 +26,12 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+# dram__bytes_read.sum + dram__bytes_write.sum of sweep_trees_kernel, one `ncu --set full` capture of this workload
+# (profiles/r1_b_ncu_full_summary.csv): the leaf-space state is L2-resident (86 % L2 hit rate), so DRAM traffic is
+# far below the algorithmic bytes.
+NCU_DRAM_BYTES_PER_LAUNCH = 1.97e9
+NCU_SOURCE = "profiles/r1_b_ncu_full_summary.csv (ncu --set full, round 1)"
+
 METRIC = "mcmc_proposals_per_sec_full_mll"
 UNIT = "proposals/s"
 
@@ -241,12 +247,12 @@ def run_b200_arm(a, rank, local_rank, world):
     sweep_no += kt
     ca = st.read()["counters"].cpu().numpy().astype(np.float64)
     d2 = (ca - cb).sum(axis=0)
-    wd = (n + 31) // 32
-    # algorithmic bytes of the leaf-space formulation:
-    #   matvec evaluation: 8 B x extent^2          (read Binv once)            -> counters[11] * 8
-    #   accepted update  : 16 B x extent^2         (read + write Binv once)    -> counters[12] * 16
-    #   v = Z^T u        : 4 B x wd x extent       (leaf bitsets)              -> counters[13] * wd * 4
-    alg_bytes = d2[11] * 8 + d2[12] * 16 + d2[13] * wd * 4
+    # algorithmic bytes of the leaf-space formulation; only the lower triangle of B^-1 is kept:
+    #   matvec evaluation: 4 B x extent^2   (read the lower triangle once)         -> counters[11] * 4
+    #   accepted update  : 8 B x extent^2   (read + write the lower triangle once) -> counters[12] * 8
+    #   v = Z^T u        : 4 B x wd x extent (leaf bitsets)                         -> counters[13] * wd * 4
+    wd = ((n + 31) // 32 + 3) // 4 * 4
+    alg_bytes = d2[11] * 4 + d2[12] * 8 + d2[13] * wd * 4
     peak, peak_src = measured_peaks()
     ach = alg_bytes / (ms_trees / 1e3) / 1e9
     acc_rate = d2[2] / max(d2[0], 1)
@@ -255,13 +261,15 @@ def run_b200_arm(a, rank, local_rank, world):
     p_used = r["p_used"].cpu().numpy()
     roofline = {
         "bound": "hbm", "kernel": "sweep_trees_kernel", "achieved": ach, "peak": peak, "unit": "GB/s",
-        "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+        "frac": ach / peak, "traffic": NCU_DRAM_BYTES_PER_LAUNCH, "traffic_source": NCU_SOURCE, "peak_source": peak_src,
         "ms_per_launch": ms_trees / kt, "share_of_step": ms_trees / (ms_trees + ms_hyper),
         "algorithmic_bytes_per_launch": alg_bytes / kt,
         "reference_dense_model": {"bytes_per_proposal": 8.0 * n * n * (1 + acc_rate), "equivalent_gbs": ref_model_gbs,
                                   "frac_of_hbm_peak": ref_model_gbs / peak,
                                   "note": "SURVEY 8d model of the reference's N x N Woodbury state; >1 because the "
-                                          "leaf-space state is P x P (P ~ 2.5 m << N)"},
+                                          "leaf-space state is P x P (P ~ 2.3 m << N), lower triangle only, L2-resident"},
+        "note": "achieved = leaf-space algorithmic bytes / CUDA-event time; the kernel is latency-bound (ncu: L2 hit 86 %, "
+                "DRAM 3 % of peak), see DESIGN.md section 6",
         "hyper_kernel_ms_per_launch": ms_hyper / kt,
     }
 
