@@ -120,6 +120,18 @@ size_t bark_predict_scratch_bytes(const bark_mcmc_dims* dims, int64_t n_c) {
     return table_bytes(dims) + 2 * align256((size_t)dims->chains * (size_t)n_c * sizeof(double));
 }
 
+int bark_predict_mixture(const bark_mcmc_dims* dims, const void* workspace, const double* mu_s, const double* var_s,
+                         int64_t n_c, double y_mean, double y_std, int add_noise, double* mu, double* var, void* stream) {
+    BARK_CHECK_ARG(dims && workspace, "null pointer");
+    if (n_c <= 0) return BARK_OK;
+    BARK_CHECK_ARG(mu_s && var_s && mu && var, "null pointer");
+    const WsLayout lay = make_layout(*dims);
+    predict_mixture_kernel<<<(unsigned)std::min<int64_t>(ceil_div(n_c, 256), 148 * 8), 256, 0, (cudaStream_t)stream>>>(
+        lay, workspace, mu_s, var_s, n_c, y_mean, y_std, add_noise, mu, var);
+    BARK_LAUNCH_CHECK();
+    return BARK_OK;
+}
+
 int bark_predict(const bark_mcmc_dims* dims, const void* workspace, bark_nodes_soa forest, const double* candidates,
                  int64_t n_c, int mode, double y_mean, double y_std, int add_noise, double* mu, double* var,
                  void* scratch, void* stream) {

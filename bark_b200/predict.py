@@ -9,7 +9,7 @@ import numpy as np
 
 from . import _lib
 from .domain import unpack_domain
-from .forest import _as_device_f64, _ptr, _stream
+from .forest import _as_device_f64, _ptr, _stream, forest_slots
 from .sampler import ChainState, raise_for_status
 
 
@@ -35,6 +35,17 @@ class PosteriorState:
         bounds = np.zeros((d, 2))
         self.state = ChainState(forest, noise, scale, train_x, train_y, bounds, feat_types, p_cap=p_cap, device=device)
         self.num_samples = forest.shape[0]
+        # tensor-core path: slice every sample's B^-1 into int8 digit planes once (leaf-column extent <= 768)
+        st = self.state
+        self.slots = forest_slots(forest)
+        self.p_max = int(st.read()["p_used"].max().item())
+        self.prep = None
+        nbytes = int(st.lib.bark_predict_prep_bytes(C.byref(st.dims), self.slots, self.p_max)) if self.p_max <= 768 else 0
+        if nbytes:
+            torch = _lib.require_cuda()
+            self.prep = torch.empty(nbytes, dtype=torch.uint8, device=st.device)
+            _lib.check(st.lib.bark_predict_prepare(C.byref(st.dims), _ptr(st.ws), st.dforest.soa(), self.slots, self.p_max,
+                                                   _ptr(self.prep), _stream()))
 
     def check(self):
         raise_for_status(self.state.read()["status"].cpu().numpy())
@@ -47,6 +58,17 @@ class PosteriorState:
         shape = (self.num_samples, n_c) if mode == 0 else (n_c,)
         mu = torch.empty(shape, dtype=torch.float64, device=st.device)
         var = torch.empty(shape, dtype=torch.float64, device=st.device)
+        if self.prep is not None:  # int8 tcgen05 path
+            mu_s, var_s = (mu, var) if mode == 0 else (
+                torch.empty((self.num_samples, n_c), dtype=torch.float64, device=st.device),
+                torch.empty((self.num_samples, n_c), dtype=torch.float64, device=st.device))
+            _lib.check(st.lib.bark_predict_umma(C.byref(st.dims), _ptr(st.ws), _ptr(self.prep), self.slots, self.p_max,
+                                                _ptr(cand_dev), n_c, _ptr(mu_s), _ptr(var_s), _stream()))
+            if mode == 1:
+                _lib.check(st.lib.bark_predict_mixture(C.byref(st.dims), _ptr(st.ws), _ptr(mu_s), _ptr(var_s), n_c,
+                                                       float(y_mean), float(y_std), int(bool(add_noise)), _ptr(mu),
+                                                       _ptr(var), _stream()))
+            return mu, var
         nbytes = int(st.lib.bark_predict_scratch_bytes(C.byref(st.dims), n_c))
         scratch = torch.empty(max(nbytes, 8), dtype=torch.uint8, device=st.device)
         _lib.check(st.lib.bark_predict(C.byref(st.dims), _ptr(st.ws), st.dforest.soa(), _ptr(cand_dev), n_c, int(mode),

@@ -175,6 +175,19 @@ int bark_predict(const bark_mcmc_dims* dims, const void* workspace, bark_nodes_s
                  int64_t n_c, int mode, double y_mean, double y_std, int add_noise, double* mu, double* var,
                  void* scratch, void* stream);
 
+/* Tensor-core predict (leaf-column extent p_max <= 768): per posterior sample, B^-1 is sliced once into 7 int8 digit
+ * planes of a 54-bit fixed-point representation (bark_predict_prepare, into `prep`), then for every tile of 128
+ * candidates z^T B^-1 z is an exact int8 one-hot GEMM on tcgen05 with masked int32 row sums (bark_predict_umma:
+ * per-sample mu, var (samples, n_c)); bark_predict_mixture folds the samples as bark_predict mode 1 does.
+ * slots: upper bound on (active node slot + 1) over the sample forests. */
+size_t bark_predict_prep_bytes(const bark_mcmc_dims* dims, int32_t slots, int32_t p_max);
+int bark_predict_prepare(const bark_mcmc_dims* dims, const void* workspace, bark_nodes_soa forest, int32_t slots,
+                         int32_t p_max, void* prep, void* stream);
+int bark_predict_umma(const bark_mcmc_dims* dims, const void* workspace, const void* prep, int32_t slots, int32_t p_max,
+                      const double* candidates, int64_t n_c, double* mu, double* var, void* stream);
+int bark_predict_mixture(const bark_mcmc_dims* dims, const void* workspace, const double* mu_s, const double* var_s,
+                         int64_t n_c, double y_mean, double y_std, int add_noise, double* mu, double* var, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
