@@ -23,7 +23,7 @@ class PosteriorState:
     """Per-sample leaf-space state (B^-1, w = B^-1 b, column maps) of all posterior samples, resident in HBM.
     Build once, predict many candidate batches."""
 
-    def __init__(self, model, data, feat_types, d, p_cap=None, device=None):
+    def __init__(self, model, data, feat_types, d, p_cap=None, device=None, tensor_cores=True):
         forest, noise, scale = model
         forest = np.ascontiguousarray(forest).reshape(-1, *forest.shape[-2:])
         noise = np.asarray(noise, dtype=np.float64).reshape(-1)
@@ -40,7 +40,8 @@ class PosteriorState:
         self.slots = forest_slots(forest)
         self.p_max = int(st.read()["p_used"].max().item())
         self.prep = None
-        nbytes = int(st.lib.bark_predict_prep_bytes(C.byref(st.dims), self.slots, self.p_max)) if self.p_max <= 768 else 0
+        # (extents above 768 columns, or tensor_cores=False, use the FP64 gather kernel of csrc/predict.cu)
+        nbytes = int(st.lib.bark_predict_prep_bytes(C.byref(st.dims), self.slots, self.p_max)) if (tensor_cores and self.p_max <= 768) else 0
         if nbytes:
             torch = _lib.require_cuda()
             self.prep = torch.empty(nbytes, dtype=torch.uint8, device=st.device)

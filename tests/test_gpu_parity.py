@@ -373,3 +373,35 @@ def test_gram_umma_tensor_core_counts(n, n2, m):
     wantK = np.stack([scale[i].item() * ((1 / m) * want2[i].astype(np.float64)) + (1e-6 + noise[i].item()) * np.eye(n)
                       for i in range(2)])
     assert np.array_equal(K2.cpu().numpy(), wantK)
+
+
+def test_predict_both_paths_and_edges():
+    """tcgen05 int8-sliced variance and the FP64 gather kernel agree with the oracle; ragged / empty candidate sets."""
+    import torch
+    s, g = load("sampler_mixed.npz"), load("functions_mixed.npz")
+    model = (rec(s["node_samples"]), s["noise_samples"], s["scale_samples"])
+    X, y, ft = s["X"], s["y"], s["feat_types"]
+    rng = np.random.default_rng(3)
+    cand = np.vstack([g["Xp"], g["Xp"][rng.integers(len(g["Xp"]), size=200)]])  # 200+ candidates: > one 128-row tile
+    want_mu, want_var = O.forest_predict(model, (X, y), cand, ft)
+    for tc in (True, False):
+        ps = B.PosteriorState(model, (X, y), ft, cand.shape[1], tensor_cores=tc)
+        assert (ps.prep is not None) == tc
+        mu, var = ps.predict_device(torch.from_numpy(cand).cuda(), mode=0)
+        assert np.allclose(mu.cpu().numpy(), want_mu, rtol=1e-9, atol=1e-11)
+        assert np.allclose(var.cpu().numpy(), want_var, rtol=1e-8, atol=1e-11)
+        m1, v1 = ps.predict_device(torch.from_numpy(cand).cuda(), mode=1, y_mean=0.3, y_std=2.0, add_noise=True)
+        wm, wv = O.mixture_of_gaussians_as_normal(want_mu * 2.0 + 0.3, want_var * 4.0 + s["noise_samples"].reshape(-1, 1))
+        assert np.allclose(m1.cpu().numpy(), wm, rtol=1e-9, atol=1e-11) and np.allclose(v1.cpu().numpy(), wv, rtol=1e-8, atol=1e-11)
+        e_mu, e_var = ps.predict_device(torch.empty((0, cand.shape[1]), dtype=torch.float64, device="cuda"), mode=0)
+        assert e_mu.shape == (ps.num_samples, 0)
+        one_mu, _ = ps.predict_device(torch.from_numpy(cand[:1]).cuda(), mode=0)
+        assert np.allclose(one_mu.cpu().numpy(), want_mu[:, :1], rtol=1e-9, atol=1e-11)
+
+
+def test_sampler_ragged_sizes():
+    """N not a multiple of 32, a single tree, a single chain, one feature: still byte-identical to the oracle."""
+    for n, dim, m, chains in ((33, 1, 1, 1), (95, 2, 3, 2), (257, 3, 5, 1)):
+        want, trace_o, got, _ = replay_case(n=n, dim=dim, cat=0, m=m, chains=chains, warm=6, ns=1, sps=4, seed=n)
+        assert got[0].tobytes() == want[0].tobytes()
+        assert np.allclose(got[1], want[1], rtol=1e-12, atol=0)
