@@ -65,6 +65,8 @@ struct Prop {
     int sl, sr;   // child slots: newly allocated (grow) or existing (prune / change)
     int a, b;     // leaf-space columns: Z' = Z + u (e_a - e_b)^T
     double lqp;   // log q-ratio + log prior-ratio
+    unsigned depth;  // depth of the edited node (children of a grow get depth + 1)
+    int pad;
 };
 
 __device__ __forceinline__ long long next_pow2_ll(long long x) {  // bit_operations.py:5-10
@@ -98,27 +100,32 @@ __device__ __forceinline__ double log_prior_ratio_at_depth(uint32_t depth, doubl
 //   u[0..3]  : uniforms (move type, node, feature, rule)
 //   box      : shared-memory scratch, 2*d doubles, pre-filled with `bounds`
 //   cm       : this tree's leaf -> column map;   colused / P: column allocator bitmap / capacity
+// lowest free leaf column (-1 if none), found by a whole warp: P/32 <= 256 words
+__device__ __forceinline__ int warp_find_free_col(const uint32_t* colused, int P) {
+    const int lane = threadIdx.x & 31;
+    const int nwords = P / 32;
+    int fcol = -1;
+    for (int base = 0; base < nwords && fcol < 0; base += 32) {
+        const int w = base + lane;
+        const uint32_t fr = (w < nwords) ? ~colused[w] : 0u;
+        const unsigned has = __ballot_sync(0xffffffffu, fr != 0u);
+        if (has) {
+            const int src = __ffs(has) - 1;
+            const uint32_t word = __shfl_sync(0xffffffffu, fr, src);
+            fcol = (base + src) * 32 + __ffs(word) - 1;
+        }
+    }
+    return fcol;
+}
+
 //   logtab[k] = log(k), k <= L+1;  priortab[dep] = log_prior_ratio_at_depth(dep): precomputed once per launch
+//   defer_col: a grow's free column (p.a) is left at -1 for the caller to fill in later (warp_find_free_col)
 __device__ __forceinline__ Prop propose_tree_warp(const TreeSmem& T, int L, double* box, const int32_t* ft, int d,
                                                   const uint16_t* cm, const uint32_t* colused, int P,
                                                   const bark_params& prm, const double* u, unsigned* status,
-                                                  const double* logtab, const double* priortab) {
+                                                  const double* logtab, const double* priortab, bool defer_col) {
     const int lane = threadIdx.x & 31;
-    // lowest free leaf column (needed by grow), found by the whole warp: P/32 <= 256 words, 8 per lane at most
-    int fcol = -1;
-    {
-        const int nwords = P / 32;
-        for (int base = 0; base < nwords && fcol < 0; base += 32) {
-            const int w = base + lane;
-            const uint32_t fr = (w < nwords) ? ~colused[w] : 0u;
-            const unsigned has = __ballot_sync(0xffffffffu, fr != 0u);
-            if (has) {
-                const int src = __ffs(has) - 1;
-                const uint32_t word = __shfl_sync(0xffffffffu, fr, src);
-                fcol = (base + src) * 32 + __ffs(word) - 1;
-            }
-        }
-    }
+    const int fcol = defer_col ? -1 : warp_find_free_col(colused, P);
     const int nch = (L + 31) >> 5;
     uint32_t mT[8], mS[8], mI[8];
     int nT = 0, nS = 0;
@@ -146,7 +153,7 @@ __device__ __forceinline__ Prop propose_tree_warp(const TreeSmem& T, int L, doub
     }
     Prop p;
     p.move = 0; p.valid = 0; p.node = 0; p.feat = 0; p.thr = 0.f; p.sl = 0; p.sr = 0; p.a = 0; p.b = 0;
-    p.lqp = -INFINITY;
+    p.lqp = -INFINITY; p.depth = 0; p.pad = 0;
     if (lane != 0) return p;
 
     // move type ~ Categorical(weights) by inverse CDF (searchsorted(cumsum(w), r), tree_proposals.py:195)
@@ -227,6 +234,7 @@ __device__ __forceinline__ Prop propose_tree_warp(const TreeSmem& T, int L, doub
         if ((double)thr32 == hi && ft[f] == FEAT_INT) return p;
     }
 
+    p.depth = T.depth[node];
     const uint32_t depth = min(T.depth[node], (uint32_t)L);  // index into the per-depth prior table
     if (move == MOVE_GROW) {
         // first two inactive slots in ascending order (tree_proposals.py:45-58)
@@ -244,7 +252,7 @@ __device__ __forceinline__ Prop propose_tree_warp(const TreeSmem& T, int L, doub
             return p;
         }
         // free leaf column for the right child (lowest index first; found above by the whole warp)
-        if (fcol < 0) {
+        if (fcol < 0 && !defer_col) {
             atomicOr(status, BARK_ST_COL_OVERFLOW);
             return p;
         }

@@ -109,7 +109,8 @@ struct Decision {
     int accept, pad;
 };
 struct SweepCtl {  // small shared control block
-    Prop prop[2];  // double-buffered by tree parity: rank 0 may publish t+1 while a peer still holds t
+    Prop prop[2];  // double-buffered by tree parity: the generator rank publishes t+1 while t is in use
+    Prop next;     // generator rank: proposal of the next tree before its free column is fixed up
     Decision dec;
     double q, ldt, mll;
     int p_hi;
@@ -270,42 +271,74 @@ sweep_trees_kernel(WsLayout lay, void* ws, bark_nodes_soa forest, bark_params pr
     unsigned long long ph_acc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     long long ph_t = clock64();
 #endif
-    for (int t = 0; t < m; ++t) {
+    // The proposal of tree t+1 is generated by the LAST rank of the cluster while rank 0 takes the MH decision of tree t
+    // (with one CTA per chain the two simply run back to back).  Only the free column of a grow depends on that
+    // decision; it is filled in afterwards.  gen_rank stages the tree, warp 0 proposes into ctl->next.
+    const int gen_rank = R - 1;
+    auto generate = [&](int tn) {  // executed by every thread of the generator CTA
+        double un[6];
+        if (tape) {
+            for (int k = 0; k < TAPE_PER_TREE; ++k) un[k] = tape[tape_base + (size_t)tn * TAPE_PER_TREE + k];
+        } else {
+            rng_uniforms(seed, g_chain, g_sweep, (uint32_t)tn, TAPE_PER_TREE, un);
+        }
+        const int64_t gn = (chain * (int64_t)m + tn) * L;
+        __syncthreads();  // previous users of the staging buffers are done
+        for (int e = tid; e < L; e += SW_THREADS) {
+            T.is_leaf[e] = __ldcg(forest.is_leaf + gn + e);
+            T.active[e] = __ldcg(forest.active + gn + e);
+            T.feat[e] = __ldcg(forest.feature + gn + e);
+            T.left[e] = __ldcg(forest.left + gn + e);
+            T.right[e] = __ldcg(forest.right + gn + e);
+            T.parent[e] = __ldcg(forest.parent + gn + e);
+            T.depth[e] = __ldcg(forest.depth + gn + e);
+            T.thr[e] = __ldcg(forest.threshold + gn + e);
+            cm_s[e] = __ldcg(cv.colmap + (size_t)tn * L + e);
+        }
+        for (int e = tid; e < 2 * d; e += SW_THREADS) box[e] = sv.bounds[e];
         __syncthreads();
+        if (wid == 0) {
+            Prop pp = propose_tree_warp(T, L, box, ftc, d, cm_s, colused_s, P, prm, un, &sc->status, logtab, priortab, true);
+            if (lane == 0) ctl->next = pp;
+        }
+        __syncthreads();
+    };
+    auto publish = [&](int tn) {  // generator CTA, after colused_s reflects every earlier decision
+        if (wid == 0) {
+            Prop pn = ctl->next;
+            if (pn.valid && pn.move == MOVE_GROW) {
+                const int fcol = warp_find_free_col(colused_s, P);
+                if (fcol < 0) {
+                    pn.valid = 0;
+                    pn.lqp = -INFINITY;
+                    if (lane == 0) atomicOr(&sc->status, BARK_ST_COL_OVERFLOW);
+                } else {
+                    pn.a = fcol;
+                }
+            }
+            if (lane == 0) {
+#pragma unroll
+                for (int r = 0; r < SW_MAX_R; ++r)
+                    if (r < R) *cluster.map_shared_rank(&ctl->prop[tn & 1], r) = pn;
+            }
+        }
+    };
+    __syncthreads();
+    if (cr == gen_rank) {
+        generate(0);
+        publish(0);
+    }
+    csync();
+
+    for (int t = 0; t < m; ++t) {
         PHASE_MARK(11);
-        // ---- rank 0 stages the tree, its column map and the root box, and generates the proposal
         double u[6];
         if (tape) {
-            for (int k = 0; k < TAPE_PER_TREE; ++k) u[k] = tape[tape_base + (size_t)t * TAPE_PER_TREE + k];
+            u[4] = tape[tape_base + (size_t)t * TAPE_PER_TREE + 4];
         } else {
             rng_uniforms(seed, g_chain, g_sweep, (uint32_t)t, TAPE_PER_TREE, u);
         }
         const int64_t g0 = (chain * (int64_t)m + t) * L;
-        if (cr == 0) {
-            for (int e = tid; e < L; e += SW_THREADS) {
-                T.is_leaf[e] = __ldcg(forest.is_leaf + g0 + e);
-                T.active[e] = __ldcg(forest.active + g0 + e);
-                T.feat[e] = __ldcg(forest.feature + g0 + e);
-                T.left[e] = __ldcg(forest.left + g0 + e);
-                T.right[e] = __ldcg(forest.right + g0 + e);
-                T.parent[e] = __ldcg(forest.parent + g0 + e);
-                T.depth[e] = __ldcg(forest.depth + g0 + e);
-                T.thr[e] = __ldcg(forest.threshold + g0 + e);
-                cm_s[e] = __ldcg(cv.colmap + (size_t)t * L + e);
-            }
-            for (int e = tid; e < 2 * d; e += SW_THREADS) box[e] = sv.bounds[e];
-            __syncthreads();
-            PHASE_MARK(0);
-            if (wid == 0) {
-                Prop pp = propose_tree_warp(T, L, box, ftc, d, cm_s, colused_s, P, prm, u, &sc->status, logtab, priortab);
-                if (lane == 0) {
-#pragma unroll
-                    for (int r = 0; r < SW_MAX_R; ++r)
-                        if (r < R) *cluster.map_shared_rank(&ctl->prop[t & 1], r) = pp;
-                }
-            }
-        }
-        csync();  // (0) proposal visible on every CTA
         PHASE_MARK(1);
         const Prop p = ctl->prop[t & 1];
         const double cur_q = ctl->q, cur_ldt = ctl->ldt, cur_mll = ctl->mll;
@@ -316,6 +349,25 @@ sweep_trees_kernel(WsLayout lay, void* ws, bark_nodes_soa forest, bark_params pr
         int pe16 = 0, r0 = 0, r1 = 0;
         bool accept = false;
         bool use_ring = false;
+
+        if (!p.valid) {
+            // nothing to evaluate (the reference would still compute an MLL it can never accept): next proposal
+            if (tid == 0) {
+                if (trace_base && cr == 0) {
+                    trace_base[t * 3 + 0] = -INFINITY;
+                    trace_base[t * 3 + 1] = cur_mll;
+                    trace_base[t * 3 + 2] = 0.0;
+                }
+            }
+            if (t + 1 < m) {
+                if (cr == gen_rank) {
+                    generate(t + 1);
+                    publish(t + 1);
+                }
+                csync();
+            }
+            continue;
+        }
 
         if (p.valid) {
             const int a = p.a, b = p.b;
@@ -664,20 +716,33 @@ sweep_trees_kernel(WsLayout lay, void* ws, bark_nodes_soa forest, bark_params pr
                         if (r < R) *cluster.map_shared_rank(&ctl->dec, r) = dd;
                 }
             }
+            // meanwhile (or right after, with one CTA per chain) the generator rank prepares the next proposal
+            if (cr == gen_rank && t + 1 < m) generate(t + 1);
             csync();  // (2b) decision visible on every CTA
             const Decision dec = ctl->dec;
             accept = dec.accept != 0;
             new_q = dec.new_q; new_ldt = dec.new_ldt; new_mll = dec.new_mll;
             eta = dec.eta; al = dec.al; be = dec.be; ga = dec.ga; cw_d = dec.cw_d; cw_v = dec.cw_v;
+            // column allocator / extent follow the decision on every CTA, then the next proposal gets its column
+            if (accept && tid == 0) {
+                if (p.move == MOVE_GROW) {
+                    colused_s[a >> 5] |= (1u << (a & 31));
+                    if (a + 1 > ctl->p_hi) ctl->p_hi = a + 1;
+                } else if (p.move == MOVE_PRUNE) {
+                    colused_s[b >> 5] &= ~(1u << (b & 31));
+                }
+            }
+            __syncthreads();
+            if (cr == gen_rank && t + 1 < m) publish(t + 1);
         }
 
         if (tid == 0) {
             if (trace_base && cr == 0) {
-                trace_base[t * 3 + 0] = p.valid ? p.lqp : -INFINITY;
+                trace_base[t * 3 + 0] = p.lqp;
                 trace_base[t * 3 + 1] = new_mll;
                 trace_base[t * 3 + 2] = accept ? 1.0 : 0.0;
             }
-            if (p.valid) {
+            {
                 ++n_valid;
                 ++n_valid_move[p.move];
                 const unsigned long long ext = (unsigned long long)pe16;
@@ -897,7 +962,7 @@ sweep_trees_kernel(WsLayout lay, void* ws, bark_nodes_soa forest, bark_params pr
                     // forest edit (tree_proposals.py:146-183) + column bookkeeping in global memory
                     uint16_t* cm = cv.colmap + (size_t)t * L;
                     if (p.move == MOVE_GROW) {
-                        const uint32_t dep = T.depth[p.node];
+                        const uint32_t dep = p.depth;
                         for (int s2 = 0; s2 < 2; ++s2) {
                             const int64_t g = g0 + (s2 ? p.sr : p.sl);
                             forest.is_leaf[g] = 1; forest.feature[g] = 0; forest.threshold[g] = 0.f; forest.left[g] = 0;
@@ -910,7 +975,7 @@ sweep_trees_kernel(WsLayout lay, void* ws, bark_nodes_soa forest, bark_params pr
                         cm[p.sl] = (uint16_t)b;   // left child keeps the old leaf's column
                         cm[p.sr] = (uint16_t)a;   // right child takes the new column
                         cm[p.node] = NO_COL;
-                        cv.colused[a >> 5] = colused_s[a >> 5] | (1u << (a & 31));
+                        cv.colused[a >> 5] = colused_s[a >> 5];  // already updated above
                     } else if (p.move == MOVE_PRUNE) {
                         forest.active[g0 + p.sl] = 0;
                         forest.active[g0 + p.sr] = 0;
@@ -918,7 +983,7 @@ sweep_trees_kernel(WsLayout lay, void* ws, bark_nodes_soa forest, bark_params pr
                         cm[p.node] = (uint16_t)a;  // merged leaf keeps the left child's column
                         cm[p.sl] = NO_COL;
                         cm[p.sr] = NO_COL;
-                        cv.colused[b >> 5] = colused_s[b >> 5] & ~(1u << (b & 31));
+                        cv.colused[b >> 5] = colused_s[b >> 5];  // already updated above
                         cv.b[b] = 0.0;
                     } else {
                         forest.feature[g0 + p.node] = (uint32_t)p.feat;
@@ -928,13 +993,7 @@ sweep_trees_kernel(WsLayout lay, void* ws, bark_nodes_soa forest, bark_params pr
             }
             __syncthreads();  // Binv row stores of this CTA complete; colused_s / w_s readers above are done
             if (tid == 0) {
-                if (p.move == MOVE_GROW) {
-                    colused_s[a >> 5] |= (1u << (a & 31));
-                    if (a + 1 > ctl->p_hi) ctl->p_hi = a + 1;
-                } else if (p.move == MOVE_PRUNE) {
-                    colused_s[b >> 5] &= ~(1u << (b & 31));
-                    w_s[b] = 0.0;
-                }
+                if (p.move == MOVE_PRUNE) w_s[b] = 0.0;
                 ctl->q = new_q; ctl->ldt = new_ldt; ctl->mll = new_mll;
                 ++n_acc;
                 ++n_acc_move[p.move];
@@ -952,7 +1011,7 @@ sweep_trees_kernel(WsLayout lay, void* ws, bark_nodes_soa forest, bark_params pr
             }
         }
         PHASE_MARK(8);
-        if (p.valid) csync();  // (3) peer's global-memory edits visible; exchanged vectors free for reuse
+        csync();  // (3) peer's global-memory edits and the next proposal visible; exchanged vectors free for reuse
     }
     PHASE_MARK(9);
     __syncthreads();
