@@ -179,7 +179,7 @@ struct ClusterTeam {
 // Blocked symmetric sweep of the n x n SPD matrix W (lower triangle valid on entry, leading dim ld).
 //   CK, GK : scratch panels, n x NB doubles each (row-major, ld = NB);  DG : NB x NB scratch (pivot inverse).
 //   yv     : optional (FULL == false) mutable copy of a right-hand side; on exit *quad = y^T W^-1 y.
-// Returns log|W| (valid on team rank 0, every thread).  *status |= BARK_ST_NOT_SPD on a non-positive pivot.
+// Returns log|W| and *quad (valid on team rank 0, every thread).  *status |= BARK_ST_NOT_SPD on a non-positive pivot.
 template <bool FULL, class Team>
 __device__ double block_sweep(double* W, int64_t ld, int n, double* CK, double* GK, double* DG, double* yv,
                               double* quad, Smem& s, uint32_t* status, const Team& team) {
@@ -205,16 +205,26 @@ __device__ double block_sweep(double* W, int64_t ld, int n, double* CK, double* 
                 if (tid < NB) {
                     double t = 0.0;
                     if (tid < bs)
-                        for (int c = 0; c < bs; ++c) t -= s.D[tid][c] * yv[k0 + c];
+                        for (int c = 0; c < bs; ++c) t -= s.D[tid][c] * __ldcg(yv + k0 + c);
                     s.tv[tid] = t;
                 }
                 __syncthreads();
-                double part = (tid < bs) ? s.tv[tid] * yv[k0 + tid] : 0.0;
+                double part = (tid < bs) ? s.tv[tid] * __ldcg(yv + k0 + tid) : 0.0;
                 q += block_sum(part, s.red);
             }
         }
         if (rlo >= n && !FULL) break;
         team.sync();
+        if (!FULL && yv && trank != 0) {
+            // the other CTAs of the team rebuild t = Dinv y_k from the published Dinv (same products, same order)
+            if (tid < NB) {
+                double t = 0.0;
+                if (tid < bs)
+                    for (int c = 0; c < bs; ++c) t += __ldcg(DG + tid * NB + c) * __ldcg(yv + k0 + c);
+                s.tv[tid] = t;
+            }
+            __syncthreads();
+        }
         // ---- P1: pivot column panel CK (gathered) and GK = CK * Dinv, by 128-row tiles round-robin over the team
         {
             int rt = 0;
@@ -234,13 +244,13 @@ __device__ double block_sweep(double* W, int64_t ld, int n, double* CK, double* 
                 }
                 __syncthreads();
                 gemm_nt_tile<ACC_SET>(GK + (int64_t)ti * NB, NB, CK + (int64_t)ti * NB, NB, DG, NB, mr, NB, bs, false, s);
-                if (!FULL && yv && trank == 0) {
-                    // y_r -= G_r . y_k = C_r . t   (forward mode runs on a solo team)
+                if (!FULL && yv) {
+                    // y_r -= G_r . y_k = C_r . t, by the owner of the row tile
                     for (int i = ti + tid; i < ti + mr; i += THREADS) {
                         const double* ck = CK + (int64_t)i * NB;
                         double a = 0.0;
                         for (int c = 0; c < bs; ++c) a += __ldcg(ck + c) * s.tv[c];
-                        yv[i] -= a;
+                        __stcg(yv + i, __ldcg(yv + i) - a);
                     }
                 }
             }

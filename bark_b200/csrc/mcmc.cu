@@ -218,7 +218,8 @@ chain_init_kernel(WsLayout lay, void* ws, bark_nodes_soa forest, const double* _
 
 // =====================================================================================================
 // hyper step: noise/scale MH with a full re-evaluation (bark_sampler.py:266-282).
-//   hyper_eval_kernel    one CTA per chain: proposal, B' = c'I + A, forward block sweep -> MLL', MH decision
+//   hyper_eval_kernel    one cluster per chain: proposal, B' = c'I + A, forward block sweep (tiles spread over
+//                        the cluster) -> MLL', MH decision on rank 0
 //   hyper_refresh_kernel one 8-CTA cluster per chain, only for accepted chains: exact B'^-1 (full block sweep
 //                        with tiles spread over the cluster), w = B'^-1 b, q, ldt, mll  (the reference
 //                        refreshes K^-1 at the same point, :276-282)
@@ -235,12 +236,17 @@ hyper_eval_kernel(WsLayout lay, void* ws, bark_params prm, int64_t sweep_in_call
     __shared__ HyperProp hp;
     __shared__ int s_phi;
     __shared__ double s_uacc;
-    const int64_t chain = blockIdx.x;
+    la::ClusterTeam team{cooperative_groups::this_cluster()};
+    const int trank = team.rank(), tsize = team.size();
+    const int64_t chain = blockIdx.x / tsize;
     ChainView cv = chain_view(lay, ws, chain);
     ChainScalars* sc = cv.sc;
     const int tid = threadIdx.x;
     const int P = (int)lay.P, m = (int)lay.m, n = (int)lay.n;
-    if (sc->status & (BARK_ST_COL_OVERFLOW | BARK_ST_TREE_OVERFLOW | BARK_ST_HYPER_MODE)) return;
+    // status bits that stop a chain are only ever set by the previous kernels or by the (identical) proposal
+    // below, so every CTA of the cluster takes the same exit
+    // and the CTAs reach no barrier before they have all either passed or left
+    if (__ldcg(&sc->status) & (BARK_ST_COL_OVERFLOW | BARK_ST_TREE_OVERFLOW | BARK_ST_HYPER_MODE)) return;
 
     const size_t per = (size_t)(m * TAPE_PER_TREE + TAPE_PER_HYPER);
     if (tid == 0) {
@@ -262,8 +268,10 @@ hyper_eval_kernel(WsLayout lay, void* ws, bark_params prm, int64_t sweep_in_call
         for (int w = P / 32 - 1; w >= 0; --w)
             if (cv.colused[w]) { hi = w * 32 + 32 - __clz(cv.colused[w]); break; }
         s_phi = hi;
-        sc->hyper_accept = 0;
-        if (hp.status) atomicOr(&sc->status, hp.status);
+        if (trank == 0) {
+            sc->hyper_accept = 0;
+            if (hp.status) atomicOr(&sc->status, hp.status);
+        }
     }
     __syncthreads();
     if (hp.status) return;
@@ -272,12 +280,16 @@ hyper_eval_kernel(WsLayout lay, void* ws, bark_params prm, int64_t sweep_in_call
     const double c2 = sig2 * (double)m / hp.scale;
     const double yy = sc->yy, cur_mll = sc->mll;
 
-    fill_B_lower(cv.Wk, cv.A, P, ph, c2);
-    for (int k = tid; k < ph; k += la::THREADS) cv.yv[k] = cv.b[k];
-    __syncthreads();
+    // B' lower triangle, rows split over the cluster
+    for (int r = trank; r < ph; r += tsize)
+        for (int k = tid; k <= r; k += la::THREADS)
+            __stcg(cv.Wk + (size_t)r * P + k, (double)__ldcg(cv.A + (size_t)r * P + k) + (r == k ? c2 : 0.0));
+    if (trank == 0)
+        for (int k = tid; k < ph; k += la::THREADS) __stcg(cv.yv + k, cv.b[k]);
+    team.sync();
     double quad = 0.0;
-    const double logdet = la::block_sweep<false>(cv.Wk, P, ph, cv.CK, cv.GK, cv.DG, cv.yv, &quad, s, &sc->status,
-                                                 la::SoloTeam());
+    const double logdet = la::block_sweep<false>(cv.Wk, P, ph, cv.CK, cv.GK, cv.DG, cv.yv, &quad, s, &sc->status, team);
+    if (trank != 0) return;  // log|B'| and the quadratic form live on rank 0
     const double ldt2 = logdet - (double)ph * log(c2);
     const double mll2 = mll_from(yy, quad, sig2, (double)n, ldt2);
     const double log_alpha = hp.lqp + (mll2 - cur_mll);
@@ -294,8 +306,9 @@ hyper_eval_kernel(WsLayout lay, void* ws, bark_params prm, int64_t sweep_in_call
             sc->prop_scale = hp.scale;
             sc->hyper_accept = 1;
             sc->counters[4] += 1ull;
-        } else if (refresh_every > 0 && ((sweep_offset + sweep_in_call + 1) % refresh_every) == 0) {
-            // periodic exact refresh of the running state (bounds the drift of the rank-2 updates between accepted
+        } else if (refresh_every > 0 && ((sweep_offset + sweep_in_call + 1 + chain_offset + chain) % refresh_every) == 0) {
+            // periodic exact refresh of the running state, staggered over the chains so that every launch of the
+            // refresh kernel carries about chains / refresh_every clusters (bounds the drift of the rank-2 updates between accepted
             // noise/scale moves; the reference only refreshes on accept, bark_sampler.py:276-282)
             sc->prop_noise = sc->noise;
             sc->prop_scale = sc->scale;
@@ -425,8 +438,29 @@ static int pick_cluster_size(int64_t chains) {
 static cudaError_t launch_hyper(cudaStream_t st, const WsLayout& lay, void* ws, const bark_params& prm, int64_t sidx,
                                 int64_t n_sweeps, uint64_t seed, int64_t chain_offset, int64_t sweep_offset,
                                 const double* tape, double* trace) {
-    hyper_eval_kernel<<<(unsigned)lay.chains, la::THREADS, sizeof(la::Smem), st>>>(
-        lay, ws, prm, sidx, n_sweeps, seed, chain_offset, sweep_offset, tape, trace, tape ? 0 : HYPER_REFRESH_EVERY);
+    {
+        // forward sweep: as many CTAs per chain (1, 2 or 4) as fit on the GPU in one wave
+        int dev = 0, sms = 148;
+        if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        int R = 1;
+        while (R < 4 && lay.chains * (R * 2) <= sms) R *= 2;
+        cudaLaunchConfig_t ecfg = {};
+        ecfg.gridDim = dim3((unsigned)(lay.chains * R));
+        ecfg.blockDim = dim3(la::THREADS);
+        ecfg.dynamicSmemBytes = sizeof(la::Smem);
+        ecfg.stream = st;
+        cudaLaunchAttribute eattr[1];
+        eattr[0].id = cudaLaunchAttributeClusterDimension;
+        eattr[0].val.clusterDim.x = (unsigned)R;
+        eattr[0].val.clusterDim.y = 1;
+        eattr[0].val.clusterDim.z = 1;
+        ecfg.attrs = eattr;
+        ecfg.numAttrs = 1;
+        const int refresh_every = tape ? 0 : HYPER_REFRESH_EVERY;
+        cudaError_t e = cudaLaunchKernelEx(&ecfg, hyper_eval_kernel, lay, ws, prm, sidx, n_sweeps, seed, chain_offset,
+                                           sweep_offset, tape, trace, refresh_every);
+        if (e != cudaSuccess) return e;
+    }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(lay.chains * HYPER_CLUSTER));
     cfg.blockDim = dim3(la::THREADS);
