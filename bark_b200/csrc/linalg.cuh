@@ -41,6 +41,23 @@ enum { ACC_SUB = 0, ACC_SET = 1 };
 // C[0:mr, 0:nc] (-)= A[0:mr, 0:K] * B[0:nc, 0:K]^T.  Row-major, leading dimensions lda/ldb/ldc.
 // lower_only: write only entries with column <= row (diagonal tiles of a symmetric update).
 // C may alias A (same rows): all global reads of A complete before the first write of C.
+// inner product step over one staged k-panel for the first J column blocks of this thread's micro-tile
+template <int J>
+__device__ __forceinline__ void gemm_panel(double (&acc)[8][4], const Smem& s, int ty, int tx) {
+#pragma unroll 4
+    for (int kk = 0; kk < KB; ++kk) {
+        double a[8], b[J];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) a[i] = s.As[ty * 8 + i][kk];
+#pragma unroll
+        for (int j = 0; j < J; ++j) b[j] = s.Bs[tx + 32 * j][kk];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j < J; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+    }
+}
+
 template <int MODE>
 __device__ __forceinline__ void gemm_nt_tile(double* C, int64_t ldc, const double* A, int64_t lda, const double* B,
                                              int64_t ldb, int mr, int nc, int K, bool lower_only, Smem& s) {
@@ -50,10 +67,15 @@ __device__ __forceinline__ void gemm_nt_tile(double* C, int64_t ldc, const doubl
     for (int i = 0; i < 8; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+    // column blocks (of 32) this warp really needs: ragged tiles and the upper part of diagonal tiles are skipped
+    int jmax = (nc + 31) >> 5;
+    if (lower_only) jmax = min(jmax, ((ty * 8 + 7) >> 5) + 1);
+    if (ty * 8 >= mr) jmax = 0;
+    const int nrow_stage = max(mr, nc);
 
     for (int k0 = 0; k0 < K; k0 += KB) {
         __syncthreads();
-        for (int e = tid; e < TILE * KB; e += THREADS) {
+        for (int e = tid; e < nrow_stage * KB; e += THREADS) {
             const int r = e >> 5, k = e & 31;
             double va = 0.0, vb = 0.0;
             if (k0 + k < K) {
@@ -64,17 +86,12 @@ __device__ __forceinline__ void gemm_nt_tile(double* C, int64_t ldc, const doubl
             s.Bs[r][k] = vb;
         }
         __syncthreads();
-#pragma unroll 4
-        for (int kk = 0; kk < KB; ++kk) {
-            double a[8], b[4];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) a[i] = s.As[ty * 8 + i][kk];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) b[j] = s.Bs[tx + 32 * j][kk];
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-#pragma unroll
-                for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+        switch (jmax) {  // warp-uniform
+            case 4: gemm_panel<4>(acc, s, ty, tx); break;
+            case 3: gemm_panel<3>(acc, s, ty, tx); break;
+            case 2: gemm_panel<2>(acc, s, ty, tx); break;
+            case 1: gemm_panel<1>(acc, s, ty, tx); break;
+            default: break;
         }
     }
 #pragma unroll
@@ -84,7 +101,7 @@ __device__ __forceinline__ void gemm_nt_tile(double* C, int64_t ldc, const doubl
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const int c = tx + 32 * j;
-                if (c < nc && (!lower_only || c <= r)) {
+                if (j < jmax && c < nc && (!lower_only || c <= r)) {
                     double* p = C + (int64_t)r * ldc + c;
                     if (MODE == ACC_SUB)
                         __stcg(p, __ldcg(p) - acc[i][j]);
@@ -134,21 +151,24 @@ __device__ __forceinline__ bool sweep_pivot_block(Smem& s) {
         const double* rowv = rowb + (j & 1) * NB;
         double* coln = colb + ((j + 1) & 1) * NB;
         double* rown = rowb + ((j + 1) & 1) * NB;
+        // branch-free body: all shared-memory loads up front, selects instead of control flow
+        double cr[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) cr[i] = colv[r0 + 8 * i];
         const double p = colv[j];
+        const double rowc = rowv[c];
         if (tid == 0) s.piv[j] = p;
         if (!(p > 0.0)) ok = false;
         const double ip = 1.0 / p;
-        const double rc = rowv[c] * ip;
+        const double rc = rowc * ip;
+        const bool cj = (c == j);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             const int r = r0 + 8 * i;
-            double x;
-            if (r == j)
-                x = (c == j) ? -ip : rc;
-            else if (c == j)
-                x = colv[r] * ip;
-            else
-                x = v[i] - colv[r] * rc;
+            const double xg = fma(-cr[i], rc, v[i]);  // general entry
+            const double xc = cr[i] * ip;             // pivot column
+            double x = cj ? xc : xg;
+            if (r == j) x = cj ? -ip : rc;            // pivot row
             v[i] = x;
             if (c == j + 1) coln[r] = x;
             if (r == j + 1) rown[c] = x;
@@ -180,6 +200,12 @@ struct ClusterTeam {
 //   CK, GK : scratch panels, n x NB doubles each (row-major, ld = NB);  DG : NB x NB scratch (pivot inverse).
 //   yv     : optional (FULL == false) mutable copy of a right-hand side; on exit *quad = y^T W^-1 y.
 // Returns log|W| and *quad (valid on team rank 0, every thread).  *status |= BARK_ST_NOT_SPD on a non-positive pivot.
+#ifdef BARK_PHASE_TIMING
+#define LA_MARK(i) do { long long t_ = clock64(); la_ph[i] += (unsigned long long)(t_ - la_t); la_t = t_; } while (0)
+#else
+#define LA_MARK(i) do { } while (0)
+#endif
+
 template <bool FULL, class Team>
 __device__ double block_sweep(double* W, int64_t ld, int n, double* CK, double* GK, double* DG, double* yv,
                               double* quad, Smem& s, uint32_t* status, const Team& team) {
@@ -187,6 +213,10 @@ __device__ double block_sweep(double* W, int64_t ld, int n, double* CK, double* 
     const int nblk = (n + NB - 1) / NB;
     const int trank = team.rank(), tsize = team.size();
     double logdet = 0.0, q = 0.0;
+#ifdef BARK_PHASE_TIMING
+    unsigned long long la_ph[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    long long la_t = clock64();
+#endif
     for (int kb = 0; kb < nblk; ++kb) {
         const int k0 = kb * NB;
         const int bs = min(NB, n - k0);
@@ -213,8 +243,10 @@ __device__ double block_sweep(double* W, int64_t ld, int n, double* CK, double* 
                 q += block_sum(part, s.red);
             }
         }
+        LA_MARK(0);
         if (rlo >= n && !FULL) break;
         team.sync();
+        LA_MARK(1);
         if (!FULL && yv && trank != 0) {
             // the other CTAs of the team rebuild t = Dinv y_k from the published Dinv (same products, same order)
             if (tid < NB) {
@@ -255,7 +287,9 @@ __device__ double block_sweep(double* W, int64_t ld, int n, double* CK, double* 
                 }
             }
         }
+        LA_MARK(2);
         team.sync();
+        LA_MARK(3);
         // ---- P2: trailing update on the lower triangle, W_ij -= G_i C_j^T, tiles round-robin over the team
         {
             int idx = 0;
@@ -269,8 +303,10 @@ __device__ double block_sweep(double* W, int64_t ld, int n, double* CK, double* 
                 }
             }
         }
+        LA_MARK(4);
         if (FULL) {
             team.sync();
+            LA_MARK(5);
             // ---- P3: write the swept pivot column/row back: W_ik = G_i (below), W_kj = G_j^T (above), W_kk = -Dinv
             int rt = 0;
             for (int ti = 0; ti < n; ti += TILE, ++rt) {
@@ -288,7 +324,9 @@ __device__ double block_sweep(double* W, int64_t ld, int n, double* CK, double* 
                 }
             }
         }
+        LA_MARK(6);
         team.sync();
+        LA_MARK(7);
     }
     if (FULL) {
         // W currently holds -W^-1 on the lower triangle: negate and mirror (32x32 tiles through shared memory).
@@ -318,6 +356,12 @@ __device__ double block_sweep(double* W, int64_t ld, int n, double* CK, double* 
         }
         team.sync();
     }
+    LA_MARK(8);
+#ifdef BARK_PHASE_TIMING
+    if (tid == 0 && trank == 0 && (blockIdx.x / tsize) == 0)
+        printf("block_sweep full=%d n=%d team=%d: P0 %llu s %llu P1 %llu s %llu P2 %llu s %llu P3 %llu s %llu mirror %llu\n", (int)FULL,
+               n, tsize, la_ph[0], la_ph[1], la_ph[2], la_ph[3], la_ph[4], la_ph[5], la_ph[6], la_ph[7], la_ph[8]);
+#endif
     if (quad) *quad = q;
     return logdet;
 }
