@@ -6,8 +6,8 @@
 //                    yields log|W| and y^T W^-1 y in n^3/3 flops.  W is pure workspace.
 //   * FULL = true  : sweep every pivot block over the whole lower triangle: W <- W^-1 (symmetric, both
 //                    triangles written) and log|W| in n^3 flops.
-// The trailing updates are NT GEMMs on 128x128 output tiles with an 8x4 register micro-tile per thread
-// (512 threads), operands staged through shared memory; the 64x64 pivot blocks are inverted in shared
+// The trailing updates are NT GEMMs on 128x128 output tiles on the FP64 tensor pipe (mma.sync m8n8k4, 16 warps,
+// 32x32 warp tiles), operands staged through shared memory; the 64x64 pivot blocks are inverted in shared
 // memory by a scalar sweep that also produces the pivots for the log-determinant.
 //
 // Replaces np.linalg.inv / np.linalg.slogdet of src/bark/fitting/bark_sampler.py:160-161,269-270 and
@@ -26,13 +26,14 @@ constexpr int KB = 32;     // k-step staged in shared memory
 constexpr int NB = 64;     // pivot block size
 
 struct __align__(16) Smem {
-    double As[TILE][KB + 1];
-    double Bs[TILE][KB + 1];
+    double As[TILE][KB + 4];  // row stride 36 doubles: conflict-free 8 x 4 DMMA fragment loads
+    double Bs[TILE][KB + 4];
     double D[NB][NB + 1];
     double colv[NB];
     double rowv[NB];
     double piv[NB];
     double tv[NB];
+    double yacc[TILE];
     double red[32];
 };
 
@@ -41,92 +42,158 @@ enum { ACC_SUB = 0, ACC_SET = 1 };
 // C[0:mr, 0:nc] (-)= A[0:mr, 0:K] * B[0:nc, 0:K]^T.  Row-major, leading dimensions lda/ldb/ldc.
 // lower_only: write only entries with column <= row (diagonal tiles of a symmetric update).
 // C may alias A (same rows): all global reads of A complete before the first write of C.
-// inner product step over one staged k-panel for the first J column blocks of this thread's micro-tile
-template <int J>
-__device__ __forceinline__ void gemm_panel(double (&acc)[8][4], const Smem& s, int ty, int tx) {
-#pragma unroll 4
-    for (int kk = 0; kk < KB; ++kk) {
-        double a[8], b[J];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) a[i] = s.As[ty * 8 + i][kk];
-#pragma unroll
-        for (int j = 0; j < J; ++j) b[j] = s.Bs[tx + 32 * j][kk];
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-#pragma unroll
-            for (int j = 0; j < J; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
-    }
+// D (8x8) += A (8x4, row) * B (4x8, col) on the FP64 tensor pipe; lane l holds A[l/4][l%4], B[l%4][l/4],
+// D[l/4][2(l%4)], D[l/4][2(l%4)+1]
+__device__ __forceinline__ void dmma_m8n8k4(double& d0, double& d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(d0), "+d"(d1)
+                 : "d"(a), "d"(b));
 }
 
+// C[0:mr, 0:nc] (-)= A[0:mr, 0:K] * B[0:nc, 0:K]^T.  Row-major, leading dimensions lda/ldb/ldc.
+// lower_only: write only entries with column <= row (diagonal tiles of a symmetric update).
+// C may alias A (same rows): all global reads of A complete before the first write of C.
+// 16 warps in a 4 x 4 grid of 32 x 32 warp tiles, each 4 x 4 m8n8k4 DMMA tiles; operands staged through shared
+// memory with a row stride of KB + 4 doubles (conflict-free fragment loads).  8 x 8 sub-tiles that are outside the
+// ragged edge, or strictly above the diagonal of a lower_only tile, are skipped.
 template <int MODE>
 __device__ __forceinline__ void gemm_nt_tile(double* C, int64_t ldc, const double* A, int64_t lda, const double* B,
                                              int64_t ldb, int mr, int nc, int K, bool lower_only, Smem& s) {
-    const int tid = threadIdx.x, ty = tid >> 5, tx = tid & 31;
-    double acc[8][4];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int wr = warp & 3, wc = warp >> 2;  // consecutive warps (one per scheduler) differ in their row block
+    const int lr = lane >> 2, lk = lane & 3;
+    double acc[4][4][2];
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
+    for (int a = 0; a < 4; ++a)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
-    // column blocks (of 32) this warp really needs: ragged tiles and the upper part of diagonal tiles are skipped
-    int jmax = (nc + 31) >> 5;
-    if (lower_only) jmax = min(jmax, ((ty * 8 + 7) >> 5) + 1);
-    if (ty * 8 >= mr) jmax = 0;
+        for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+    unsigned on = 0;  // bit a*4+b: sub-tile (a, b) of this warp is needed (warp-uniform)
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const int rlo = 32 * wr + 8 * a, clo = 32 * wc + 8 * b;
+            if (rlo < mr && clo < nc && (!lower_only || clo <= rlo + 7)) on |= 1u << (a * 4 + b);
+        }
     const int nrow_stage = max(mr, nc);
 
     for (int k0 = 0; k0 < K; k0 += KB) {
-        __syncthreads();
-        for (int e = tid; e < nrow_stage * KB; e += THREADS) {
+        // all global loads first (8 + 8 per thread in flight), then the shared-memory stores
+        double va[TILE * KB / THREADS], vb[TILE * KB / THREADS];
+#pragma unroll
+        for (int it = 0; it < TILE * KB / THREADS; ++it) {
+            const int e = tid + it * THREADS;
             const int r = e >> 5, k = e & 31;
-            double va = 0.0, vb = 0.0;
+            va[it] = 0.0;
+            vb[it] = 0.0;
             if (k0 + k < K) {
-                if (r < mr) va = __ldcg(A + (int64_t)r * lda + k0 + k);
-                if (r < nc) vb = __ldcg(B + (int64_t)r * ldb + k0 + k);
+                if (r < mr) va[it] = __ldcg(A + (int64_t)r * lda + k0 + k);
+                if (r < nc) vb[it] = __ldcg(B + (int64_t)r * ldb + k0 + k);
             }
-            s.As[r][k] = va;
-            s.Bs[r][k] = vb;
         }
         __syncthreads();
-        switch (jmax) {  // warp-uniform
-            case 4: gemm_panel<4>(acc, s, ty, tx); break;
-            case 3: gemm_panel<3>(acc, s, ty, tx); break;
-            case 2: gemm_panel<2>(acc, s, ty, tx); break;
-            case 1: gemm_panel<1>(acc, s, ty, tx); break;
-            default: break;
+#pragma unroll
+        for (int it = 0; it < TILE * KB / THREADS; ++it) {
+            const int e = tid + it * THREADS;
+            const int r = e >> 5, k = e & 31;
+            if (r < nrow_stage) {
+                s.As[r][k] = va[it];
+                s.Bs[r][k] = vb[it];
+            }
+        }
+        __syncthreads();
+        if (on) {
+            const int kend = min(KB, (K - k0 + 3) & ~3);
+#pragma unroll 2
+            for (int kk = 0; kk < kend; kk += 4) {
+                double a[4], b[4];
+#pragma unroll
+                for (int x = 0; x < 4; ++x) {
+                    a[x] = s.As[32 * wr + 8 * x + lr][kk + lk];
+                    b[x] = s.Bs[32 * wc + 8 * x + lr][kk + lk];
+                }
+#pragma unroll
+                for (int x = 0; x < 4; ++x)
+#pragma unroll
+                    for (int y = 0; y < 4; ++y)
+                        if (on & (1u << (x * 4 + y))) dmma_m8n8k4(acc[x][y][0], acc[x][y][1], a[x], b[y]);
+            }
         }
     }
+    // epilogue in two halves of 8 sub-tiles: all loads of C first, then the stores (C is only ever touched by its
+    // owner thread, so the order is free)
+    const bool vec_ok = ((reinterpret_cast<uintptr_t>(C) | (uintptr_t)(ldc * 8)) & 15) == 0;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const int r = ty * 8 + i;
-        if (r < mr) {
+    for (int xh = 0; xh < 4; xh += 2) {
+        double old[2][4][2];
+        if (MODE == ACC_SUB) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int c = tx + 32 * j;
-                if (j < jmax && c < nc && (!lower_only || c <= r)) {
-                    double* p = C + (int64_t)r * ldc + c;
-                    if (MODE == ACC_SUB)
-                        __stcg(p, __ldcg(p) - acc[i][j]);
-                    else
-                        __stcg(p, acc[i][j]);
+            for (int xx = 0; xx < 2; ++xx)
+#pragma unroll
+                for (int y = 0; y < 4; ++y) {
+                    const int x = xh + xx;
+                    old[xx][y][0] = old[xx][y][1] = 0.0;
+                    if (!(on & (1u << (x * 4 + y)))) continue;
+                    const int r = 32 * wr + 8 * x + lr, c = 32 * wc + 8 * y + 2 * lk;
+                    if (r >= mr) continue;
+                    const double* p = C + (int64_t)r * ldc + c;
+                    const bool ok0 = c < nc && (!lower_only || c <= r);
+                    const bool ok1 = c + 1 < nc && (!lower_only || c + 1 <= r);
+                    if (ok0 && ok1 && vec_ok) {
+                        const double2 o = __ldcg(reinterpret_cast<const double2*>(p));
+                        old[xx][y][0] = o.x;
+                        old[xx][y][1] = o.y;
+                    } else {
+                        if (ok0) old[xx][y][0] = __ldcg(p);
+                        if (ok1) old[xx][y][1] = __ldcg(p + 1);
+                    }
+                }
+        }
+#pragma unroll
+        for (int xx = 0; xx < 2; ++xx)
+#pragma unroll
+            for (int y = 0; y < 4; ++y) {
+                const int x = xh + xx;
+                if (!(on & (1u << (x * 4 + y)))) continue;
+                const int r = 32 * wr + 8 * x + lr, c = 32 * wc + 8 * y + 2 * lk;
+                if (r >= mr) continue;
+                double* p = C + (int64_t)r * ldc + c;
+                const bool ok0 = c < nc && (!lower_only || c <= r);
+                const bool ok1 = c + 1 < nc && (!lower_only || c + 1 <= r);
+                const double v0 = (MODE == ACC_SUB) ? old[xx][y][0] - acc[x][y][0] : acc[x][y][0];
+                const double v1 = (MODE == ACC_SUB) ? old[xx][y][1] - acc[x][y][1] : acc[x][y][1];
+                if (ok0 && ok1 && vec_ok) {
+                    __stcg(reinterpret_cast<double2*>(p), make_double2(v0, v1));
+                } else {
+                    if (ok0) __stcg(p, v0);
+                    if (ok1) __stcg(p + 1, v1);
                 }
             }
-        }
     }
 }
 
 // Load the bs x bs diagonal block at G (lower triangle valid) into s.D, symmetrised, identity-padded to NB.
 __device__ __forceinline__ void load_pivot_block(const double* G, int64_t ld, int bs, Smem& s) {
-    for (int e = threadIdx.x; e < NB * NB; e += THREADS) {
+    double v[NB * NB / THREADS];  // all loads in flight before the first shared-memory store
+#pragma unroll
+    for (int it = 0; it < NB * NB / THREADS; ++it) {
+        const int e = threadIdx.x + it * THREADS;
         const int r = e / NB, c = e % NB;
-        double v;
         if (r < bs && c < bs)
-            v = (c <= r) ? __ldcg(G + (int64_t)r * ld + c) : __ldcg(G + (int64_t)c * ld + r);
+            v[it] = (c <= r) ? __ldcg(G + (int64_t)r * ld + c) : __ldcg(G + (int64_t)c * ld + r);
         else
-            v = (r == c) ? 1.0 : 0.0;
-        s.D[r][c] = v;
+            v[it] = (r == c) ? 1.0 : 0.0;
+    }
+#pragma unroll
+    for (int it = 0; it < NB * NB / THREADS; ++it) {
+        const int e = threadIdx.x + it * THREADS;
+        s.D[e / NB][e % NB] = v[it];
     }
     __syncthreads();
 }
 
+// (A two-level variant -- sweep a 64 x 32 panel, Schur complement, sweep the 32 x 32 rest -- halves the serial
+// cost but was measured 5-100x less accurate for the in-place inverse at bench scale, so the direct sweep stays.)
 // Scalar symmetric sweep of s.D over all NB pivots: s.D <- -D^-1, s.piv[j] <- j-th pivot (successive
 // Schur complements; their product is det D).  Returns false (uniformly) if a pivot is not positive.
 // Register-resident: every thread owns 8 fixed entries (rows r0 + 8 i, column c) of the 64 x 64 block and only
@@ -214,7 +281,7 @@ __device__ double block_sweep(double* W, int64_t ld, int n, double* CK, double* 
     const int trank = team.rank(), tsize = team.size();
     double logdet = 0.0, q = 0.0;
 #ifdef BARK_PHASE_TIMING
-    unsigned long long la_ph[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    unsigned long long la_ph[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     long long la_t = clock64();
 #endif
     for (int kb = 0; kb < nblk; ++kb) {
@@ -224,22 +291,27 @@ __device__ double block_sweep(double* W, int64_t ld, int n, double* CK, double* 
         // ---- P0 (rank 0): invert the pivot block in shared memory, publish Dinv, eliminate the right-hand side
         if (trank == 0) {
             load_pivot_block(W + (int64_t)k0 * ld + k0, ld, bs, s);
+            LA_MARK(10);
             const bool ok = sweep_pivot_block(s);  // s.D = -Dinv
+            LA_MARK(11);
             if (!ok && tid == 0 && status) atomicOr(status, BARK_ST_NOT_SPD);
             {
                 double lg = (tid < NB) ? log(s.piv[tid]) : 0.0;
                 logdet += block_sum(lg, s.red);
             }
             for (int e = tid; e < NB * NB; e += THREADS) __stcg(DG + e, -s.D[e / NB][e % NB]);
+            LA_MARK(12);
             if (!FULL && yv) {
+                if (tid < NB) s.colv[tid] = (tid < bs) ? __ldcg(yv + k0 + tid) : 0.0;
+                __syncthreads();
                 if (tid < NB) {
                     double t = 0.0;
                     if (tid < bs)
-                        for (int c = 0; c < bs; ++c) t -= s.D[tid][c] * __ldcg(yv + k0 + c);
+                        for (int c = 0; c < bs; ++c) t -= s.D[tid][c] * s.colv[c];
                     s.tv[tid] = t;
                 }
                 __syncthreads();
-                double part = (tid < bs) ? s.tv[tid] * __ldcg(yv + k0 + tid) : 0.0;
+                double part = (tid < bs) ? s.tv[tid] * s.colv[tid] : 0.0;
                 q += block_sum(part, s.red);
             }
         }
@@ -249,10 +321,14 @@ __device__ double block_sweep(double* W, int64_t ld, int n, double* CK, double* 
         LA_MARK(1);
         if (!FULL && yv && trank != 0) {
             // the other CTAs of the team rebuild t = Dinv y_k from the published Dinv (same products, same order)
+            if (tid < NB) s.colv[tid] = (tid < bs) ? __ldcg(yv + k0 + tid) : 0.0;
+            __syncthreads();
             if (tid < NB) {
                 double t = 0.0;
-                if (tid < bs)
-                    for (int c = 0; c < bs; ++c) t += __ldcg(DG + tid * NB + c) * __ldcg(yv + k0 + c);
+                if (tid < bs) {
+#pragma unroll 16
+                    for (int c = 0; c < bs; ++c) t += __ldcg(DG + tid * NB + c) * s.colv[c];
+                }
                 s.tv[tid] = t;
             }
             __syncthreads();
@@ -263,28 +339,43 @@ __device__ double block_sweep(double* W, int64_t ld, int n, double* CK, double* 
             for (int ti = rlo; ti < n; ti += TILE, ++rt) {
                 if (rt % tsize != trank) continue;
                 const int mr = min(TILE, n - ti);
-                for (int e = tid; e < mr * NB; e += THREADS) {
-                    const int i = ti + e / NB, c = e % NB;
-                    double v = 0.0;
-                    if (c < bs) {
-                        if (i >= k0 + bs)
-                            v = __ldcg(W + (int64_t)i * ld + k0 + c);
-                        else if (i < k0)
-                            v = __ldcg(W + (int64_t)(k0 + c) * ld + i);
+                const bool do_y = !FULL && yv;
+                if (do_y && tid < TILE) s.yacc[tid] = 0.0;
+                if (do_y) __syncthreads();
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    // 8 gathered entries per thread in flight, then the stores; a warp covers half a panel row,
+                    // so the row's dot product with t is a warp sum
+                    double v[8];
+#pragma unroll
+                    for (int it = 0; it < 8; ++it) {
+                        const int e = tid + (half * 8 + it) * THREADS;
+                        const int i = ti + e / NB, c = e % NB;
+                        v[it] = 0.0;
+                        if (e < mr * NB && c < bs) {
+                            if (i >= k0 + bs)
+                                v[it] = __ldcg(W + (int64_t)i * ld + k0 + c);
+                            else if (i < k0)
+                                v[it] = __ldcg(W + (int64_t)(k0 + c) * ld + i);
+                        }
                     }
-                    __stcg(CK + (int64_t)i * NB + c, v);
+#pragma unroll
+                    for (int it = 0; it < 8; ++it) {
+                        const int e = tid + (half * 8 + it) * THREADS;
+                        const int i = ti + e / NB, c = e % NB;
+                        if (e < mr * NB) __stcg(CK + (int64_t)i * NB + c, v[it]);
+                        if (do_y) {
+                            const double part = warp_sum(v[it] * s.tv[c]);
+                            if ((tid & 31) == 0 && e < mr * NB) atomicAdd(&s.yacc[e / NB], part);
+                        }
+                    }
                 }
                 __syncthreads();
-                gemm_nt_tile<ACC_SET>(GK + (int64_t)ti * NB, NB, CK + (int64_t)ti * NB, NB, DG, NB, mr, NB, bs, false, s);
-                if (!FULL && yv) {
+                if (do_y) {
                     // y_r -= G_r . y_k = C_r . t, by the owner of the row tile
-                    for (int i = ti + tid; i < ti + mr; i += THREADS) {
-                        const double* ck = CK + (int64_t)i * NB;
-                        double a = 0.0;
-                        for (int c = 0; c < bs; ++c) a += __ldcg(ck + c) * s.tv[c];
-                        __stcg(yv + i, __ldcg(yv + i) - a);
-                    }
+                    for (int i = tid; i < mr; i += THREADS) __stcg(yv + ti + i, __ldcg(yv + ti + i) - s.yacc[i]);
                 }
+                gemm_nt_tile<ACC_SET>(GK + (int64_t)ti * NB, NB, CK + (int64_t)ti * NB, NB, DG, NB, mr, NB, bs, false, s);
             }
         }
         LA_MARK(2);
@@ -312,15 +403,33 @@ __device__ double block_sweep(double* W, int64_t ld, int n, double* CK, double* 
             for (int ti = 0; ti < n; ti += TILE, ++rt) {
                 if (rt % tsize != trank) continue;
                 const int mr = min(TILE, n - ti);
-                for (int e = tid; e < mr * NB; e += THREADS) {
-                    const int i = ti + e / NB, c = e % NB;
-                    if (c >= bs) continue;
-                    if (i >= k0 + bs)
-                        __stcg(W + (int64_t)i * ld + k0 + c, __ldcg(GK + (int64_t)i * NB + c));
-                    else if (i < k0)
-                        __stcg(W + (int64_t)(k0 + c) * ld + i, __ldcg(GK + (int64_t)i * NB + c));
-                    else if (c <= i - k0)
-                        __stcg(W + (int64_t)i * ld + k0 + c, -__ldcg(DG + (i - k0) * NB + c));
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    double v[8];
+#pragma unroll
+                    for (int it = 0; it < 8; ++it) {
+                        const int e = tid + (half * 8 + it) * THREADS;
+                        const int i = ti + e / NB, c = e % NB;
+                        v[it] = 0.0;
+                        if (e < mr * NB && c < bs) {
+                            if (i >= k0 + bs || i < k0)
+                                v[it] = __ldcg(GK + (int64_t)i * NB + c);
+                            else if (c <= i - k0)
+                                v[it] = -__ldcg(DG + (i - k0) * NB + c);
+                        }
+                    }
+#pragma unroll
+                    for (int it = 0; it < 8; ++it) {
+                        const int e = tid + (half * 8 + it) * THREADS;
+                        const int i = ti + e / NB, c = e % NB;
+                        if (e >= mr * NB || c >= bs) continue;
+                        if (i >= k0 + bs)
+                            __stcg(W + (int64_t)i * ld + k0 + c, v[it]);
+                        else if (i < k0)
+                            __stcg(W + (int64_t)(k0 + c) * ld + i, v[it]);
+                        else if (c <= i - k0)
+                            __stcg(W + (int64_t)i * ld + k0 + c, v[it]);
+                    }
                 }
             }
         }
@@ -359,8 +468,8 @@ __device__ double block_sweep(double* W, int64_t ld, int n, double* CK, double* 
     LA_MARK(8);
 #ifdef BARK_PHASE_TIMING
     if (tid == 0 && trank == 0 && (blockIdx.x / tsize) == 0)
-        printf("block_sweep full=%d n=%d team=%d: P0 %llu s %llu P1 %llu s %llu P2 %llu s %llu P3 %llu s %llu mirror %llu\n", (int)FULL,
-               n, tsize, la_ph[0], la_ph[1], la_ph[2], la_ph[3], la_ph[4], la_ph[5], la_ph[6], la_ph[7], la_ph[8]);
+        printf("block_sweep full=%d n=%d team=%d: P0 %llu s %llu P1 %llu s %llu P2 %llu s %llu P3 %llu s %llu mirror %llu | P0: load %llu sweep %llu logdet+DG %llu rest %llu\n", (int)FULL,
+               n, tsize, la_ph[0], la_ph[1], la_ph[2], la_ph[3], la_ph[4], la_ph[5], la_ph[6], la_ph[7], la_ph[8], la_ph[10], la_ph[11], la_ph[12], la_ph[0]);
 #endif
     if (quad) *quad = q;
     return logdet;

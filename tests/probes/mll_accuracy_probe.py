@@ -1,7 +1,7 @@
 """Accuracy of the running (leaf-space) log-MLL and of the from-scratch GPU MLL at bench scale, against a
 float64 LAPACK Cholesky and a longdouble-refined value on the host (diagnostic; run on a GPU box)."""
 import sys, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, torch
 import bark_b200 as B
 from bark_b200 import synthetic
