@@ -384,28 +384,49 @@ sweep_trees_kernel(WsLayout lay, void* ws, bark_nodes_soa forest, bark_params pr
             const uint32_t* bits_b = cv.bits + (size_t)b * wd;
             const double* xf = sv.Xt + (size_t)p.feat * npad;
             const int ftype = ftc[p.feat];
-            for (int i = tid; i < npad; i += SW_THREADS) {
-                const int w = i >> 5;
-                bool pos = false, neg = false;
-                if (i < n) {
-                    const bool in_b = (__ldcg(bits_b + w) >> lane) & 1u;
-                    if (p.move == MOVE_GROW) {
-                        if (in_b) pos = !goes_left(xf[i], p.thr, ftype);
-                    } else if (p.move == MOVE_PRUNE) {
-                        pos = in_b;
-                    } else {  // change: b = left child's column, a = right child's column
-                        const bool in_a = (__ldcg(bits_a + w) >> lane) & 1u;
-                        if (in_a || in_b) {
-                            const bool gl = goes_left(xf[i], p.thr, ftype);
-                            pos = in_b && !gl;
-                            neg = in_a && gl;
+            // four points per thread at a time: all global loads are issued before the first shared-memory store
+            for (int base = 0; base < npad; base += 4 * SW_THREADS) {
+                uint32_t wa[4], wb[4];
+                double xv[4], yv[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int i = base + u * SW_THREADS + tid;
+                    wa[u] = wb[u] = 0u;
+                    xv[u] = yv[u] = 0.0;
+                    if (i < npad) {
+                        wb[u] = __ldcg(bits_b + (i >> 5));
+                        if (p.move == MOVE_CHANGE) wa[u] = __ldcg(bits_a + (i >> 5));
+                        if (i < n) {
+                            xv[u] = xf[i];
+                            yv[u] = sv.y[i];
                         }
                     }
-                    if (pos) { eta_part += sv.y[i]; cnt_part += 1.0; }
-                    if (neg) { eta_part -= sv.y[i]; cnt_part += 1.0; }
                 }
-                const unsigned bp = __ballot_sync(0xffffffffu, pos), bn = __ballot_sync(0xffffffffu, neg);
-                if (lane == 0) { upos[w] = bp; uneg[w] = bn; }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int i = base + u * SW_THREADS + tid;
+                    if (i >= npad) break;  // warp-uniform (npad is a multiple of 32)
+                    bool pos = false, neg = false;
+                    if (i < n) {
+                        const bool in_b = (wb[u] >> lane) & 1u;
+                        if (p.move == MOVE_GROW) {
+                            if (in_b) pos = !goes_left(xv[u], p.thr, ftype);
+                        } else if (p.move == MOVE_PRUNE) {
+                            pos = in_b;
+                        } else {  // change: b = left child's column, a = right child's column
+                            const bool in_a = (wa[u] >> lane) & 1u;
+                            if (in_a || in_b) {
+                                const bool gl = goes_left(xv[u], p.thr, ftype);
+                                pos = in_b && !gl;
+                                neg = in_a && gl;
+                            }
+                        }
+                        if (pos) { eta_part += yv[u]; cnt_part += 1.0; }
+                        if (neg) { eta_part -= yv[u]; cnt_part += 1.0; }
+                    }
+                    const unsigned bp = __ballot_sync(0xffffffffu, pos), bn = __ballot_sync(0xffffffffu, neg);
+                    if (lane == 0) { upos[i >> 5] = bp; uneg[i >> 5] = bn; }
+                }
             }
             block_sum2(eta_part, cnt_part, red);  // counts are exact (integers < 2^53)
             eta = eta_part;
