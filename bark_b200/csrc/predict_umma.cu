@@ -3,11 +3,14 @@
 //   var_s(x) = sig_s * z^T Binv_s z,   z = one-hot leaf indicator of the candidate (m ones among P columns).
 // Binv_s is turned once per posterior sample into 7 signed base-256 digit planes of a 54-bit fixed-point
 // representation (|Binv| <= 1/c bounds the scale):  Binv = 2^-shift * sum_k 256^k D_k,  D_k int8.
-// For a tile of 128 candidates the CTA builds the one-hot A operand in shared memory while it walks the trees
-// (mean = sum_t w[col_t] on the way), then T_k = Zc * D_k runs on tcgen05 (kind::i8, s32 accumulators in TMEM,
-// M = 128, N = 64 per digit plane -> 7 x 64 = 448 TMEM columns), the digit tiles streamed by the bulk-copy engine.
+// For a tile of 128 candidates the CTA walks the trees with three threads per candidate (leaf columns collected as
+// a bit mask per row, mean = sum_t w[col_t] on the way), expands the masks into the one-hot int8 A operand in
+// shared memory, then T_k = Zc * D_k runs on tcgen05 (kind::i8, s32 accumulators in TMEM, M = 128, N = 256 per
+// instruction: with both operands in shared memory a small N is bound by re-reading A), one (column tile, digit
+// plane) item at a time into one of two 256-column TMEM buffers, the digit tiles streamed by the bulk-copy engine.
 // The epilogue never needs T itself: z^T Binv z = sum_k 256^k * (sum over the candidate's own columns of T_k),
-// i.e. 7 masked int32 row sums (exact), combined once in FP64.  No n_c x P matrix ever exists in memory.
+// i.e. 7 masked int32 row sums (exact), combined once in FP64; it drains one TMEM buffer while the tensor core
+// fills the other.  No n_c x P matrix ever exists in memory.
 //
 // Replaces  scale - diag(K_xX K^-1 K_Xx)  of src/bark/tree_kernels/tree_gps.py:103-112.
 #include <algorithm>
@@ -19,14 +22,15 @@
 namespace bark {
 
 constexpr int PU_ROWS = 128;        // candidates per CTA (UMMA M)
-constexpr int PU_N = 64;            // Binv columns per accumulator tile (UMMA N); 7 x 64 = 448 TMEM columns
+constexpr int PU_N = 256;           // Binv columns per accumulator tile (UMMA N); two TMEM buffers of 256 columns
 constexpr int PU_KB = 128;          // K bytes per operand tile (one SWIZZLE_128B atom row)
 constexpr int PU_SLICES = 7;        // base-256 digit planes
-constexpr int PU_MAX_STAGES = 4;    // ring stages; one stage = all K tiles of one (column tile, digit plane)
-constexpr int PU_THREADS = 192;     // warps 0-3: walk + epilogue, warp 4: MMA issue, warp 5: TMA producer
+constexpr int PU_MAX_STAGES = 4;    // ring stages; one stage = one K tile of one (column tile, digit plane)
+constexpr int PU_WALK_GROUPS = 3;   // threads per candidate in the walk (trees t = g mod 3)
+constexpr int PU_THREADS = 448;     // warps 0-3: walk + epilogue, 4: MMA issue, 5: TMA producer, 6-13: walk
 constexpr int PU_A_TILE = PU_ROWS * PU_KB;  // 16 KB
-constexpr int PU_B_TILE = PU_N * PU_KB;     // 8 KB
-constexpr int PU_RING_MAX = 96 * 1024;
+constexpr int PU_B_TILE = PU_N * PU_KB;     // 32 KB
+constexpr int PU_RING_MAX = 128 * 1024;
 constexpr int PU_MAX_P = 768;
 
 __device__ __forceinline__ uint32_t pu_smem(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -43,7 +47,7 @@ __host__ __device__ inline PrepLayout prep_layout(int64_t samples, int64_t m, in
     PrepLayout l;
     l.hi = slots;
     l.kt = (p_max + PU_KB - 1) / PU_KB;
-    l.nt = (p_max + PU_N - 1) / PU_N;
+    l.nt = (l.kt * PU_KB + PU_N - 1) / PU_N;  // the last column tile may be half full (N = 128)
     size_t o = 0;
     l.off_table = o; o = align256(o + (size_t)samples * m * slots * sizeof(WalkNode));
     l.off_tiles = o; o = align256(o + (size_t)samples * l.nt * PU_SLICES * l.kt * PU_B_TILE);
@@ -76,7 +80,7 @@ __global__ void pu_slice_kernel(WsLayout lay, const void* ws, int kt_n, int nt_n
     frexp(1.0 / c, &e);
     const int shift = 53 - e;
     if (blockIdx.x == 0 && threadIdx.x == 0) scale_out[sample] = ldexp(1.0, -shift);
-    const int64_t Q = (int64_t)nt_n * PU_N, K = (int64_t)kt_n * PU_KB, P = lay.P;
+    const int64_t K = (int64_t)kt_n * PU_KB, Q = K, P = lay.P;
     uint8_t* base = tiles + (size_t)sample * nt_n * PU_SLICES * kt_n * PU_B_TILE;
     for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < Q * K; idx += (int64_t)gridDim.x * blockDim.x) {
         const int64_t q = idx / K, k = idx % K;
@@ -160,21 +164,32 @@ __device__ __forceinline__ void pu_tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) 
 }
 
 struct PuSmem {
-    size_t off_a, off_ring, off_table, off_zmask, off_w, off_xs, off_ft, off_bars, total;
+    size_t off_a, off_ring, off_table, off_zmask, off_w, off_xs, off_ft, off_mean, off_bars, total;
 };
-__host__ __device__ inline PuSmem pu_smem_layout(int m, int hi, int d, int kt, int nt, int ring_bytes) {
+__host__ __device__ inline PuSmem pu_smem_layout(int m, int hi, int d, int kt, int ring_bytes) {
     PuSmem s;
     size_t o = 0;
     s.off_a = o;      o += (size_t)kt * PU_A_TILE;
     s.off_ring = o;   o += (size_t)ring_bytes;
     s.off_table = o;  o = align256(o + (size_t)m * hi * sizeof(WalkNode));
-    s.off_zmask = o;  o = align256(o + (size_t)PU_ROWS * nt * 8);
+    s.off_zmask = o;  o = align256(o + (size_t)PU_ROWS * kt * 2 * 8);  // [64-column word][row]
     s.off_w = o;      o = align256(o + (size_t)kt * PU_KB * 8);
     s.off_xs = o;     o = align256(o + (size_t)d * (PU_ROWS + 1) * 8);
     s.off_ft = o;     o = align256(o + (size_t)d * 4);
-    s.off_bars = o;   o = align256(o + (size_t)(2 * PU_MAX_STAGES + 2) * 8 + 16);
+    s.off_mean = o;   o = align256(o + (size_t)PU_WALK_GROUPS * PU_ROWS * 8);
+    s.off_bars = o;   o = align256(o + (size_t)(2 * PU_MAX_STAGES + 4) * 8 + 16);
     s.total = o;
     return s;
+}
+
+// 16 mask bits -> 16 bytes of 0 / 1 (x * 0x00204081 spreads 4 bits over the low bits of 4 bytes)
+__device__ __forceinline__ uint4 pu_expand16(uint32_t b) {
+    uint4 r;
+    r.x = ((b & 0xFu) * 0x00204081u) & 0x01010101u;
+    r.y = (((b >> 4) & 0xFu) * 0x00204081u) & 0x01010101u;
+    r.z = (((b >> 8) & 0xFu) * 0x00204081u) & 0x01010101u;
+    r.w = (((b >> 12) & 0xFu) * 0x00204081u) & 0x01010101u;
+    return r;
 }
 
 __global__ void __launch_bounds__(PU_THREADS, 1)
@@ -184,21 +199,22 @@ predict_umma_kernel(WsLayout lay, const void* ws, const WalkNode* __restrict__ t
                     int64_t n_c, double* __restrict__ mu, double* __restrict__ var) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     const int d = (int)lay.d, m = (int)lay.m;
-    const PuSmem sl = pu_smem_layout(m, hi, d, kt_n, nt_n, ring_bytes);
+    const PuSmem sl = pu_smem_layout(m, hi, d, kt_n, ring_bytes);
     unsigned char* a_tiles = smem_raw + sl.off_a;
     unsigned char* ring = smem_raw + sl.off_ring;
     WalkNode* tb = reinterpret_cast<WalkNode*>(smem_raw + sl.off_table);
-    unsigned long long* zmask = reinterpret_cast<unsigned long long*>(smem_raw + sl.off_zmask);  // [row][nt]
+    unsigned long long* zmask = reinterpret_cast<unsigned long long*>(smem_raw + sl.off_zmask);  // [word][row]
     double* w_s = reinterpret_cast<double*>(smem_raw + sl.off_w);
     double* xs = reinterpret_cast<double*>(smem_raw + sl.off_xs);  // [d][PU_ROWS + 1]
     int* ftc = reinterpret_cast<int*>(smem_raw + sl.off_ft);
+    double* meanp = reinterpret_cast<double*>(smem_raw + sl.off_mean);  // [group][row]
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_raw + sl.off_bars);
     uint64_t* empty_bar = full_bar + PU_MAX_STAGES;
-    uint64_t* acc_full = empty_bar + PU_MAX_STAGES;
-    uint64_t* acc_free = acc_full + 1;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_free + 1);
-    const uint32_t stage_bytes = (uint32_t)kt_n * PU_B_TILE;
-    const int nstages = min(PU_MAX_STAGES, (int)((uint32_t)ring_bytes / stage_bytes));
+    uint64_t* acc_full = empty_bar + PU_MAX_STAGES;  // [2]
+    uint64_t* acc_free = acc_full + 2;               // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_free + 2);
+    const int nstages = min(PU_MAX_STAGES, ring_bytes / PU_B_TILE);
+    const int nwords = kt_n * 2;  // 64-column mask words per candidate row
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int64_t sample = blockIdx.y;
@@ -210,8 +226,7 @@ predict_umma_kernel(WsLayout lay, const void* ws, const WalkNode* __restrict__ t
     // ---- setup: barriers, TMEM, staging of the sample's trees / w and of the candidate tile
     if (tid == 0) {
         for (int s = 0; s < PU_MAX_STAGES; ++s) { pu_mbar_init(full_bar + s, 1); pu_mbar_init(empty_bar + s, 1); }
-        pu_mbar_init(acc_full, 1);
-        pu_mbar_init(acc_free, PU_ROWS);
+        for (int b = 0; b < 2; ++b) { pu_mbar_init(acc_full + b, 1); pu_mbar_init(acc_free + b, PU_ROWS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 4) {
@@ -225,75 +240,103 @@ predict_umma_kernel(WsLayout lay, const void* ws, const WalkNode* __restrict__ t
         for (int e = tid; e < kt_n * PU_KB; e += PU_THREADS) w_s[e] = (e < lay.P) ? cv.w[e] : 0.0;
         for (int e = tid; e < np * d; e += PU_THREADS) xs[(size_t)(e % d) * (PU_ROWS + 1) + e / d] = cand[p0 * d + e];
         for (int e = tid; e < d; e += PU_THREADS) ftc[e] = sv.ft[e];
-        uint4* az = reinterpret_cast<uint4*>(a_tiles);
-        for (int e = tid; e < kt_n * PU_A_TILE / 16; e += PU_THREADS) az[e] = make_uint4(0, 0, 0, 0);
-        for (int e = tid; e < PU_ROWS * nt_n; e += PU_THREADS) zmask[e] = 0ull;
+        for (int e = tid; e < PU_ROWS * nwords; e += PU_THREADS) zmask[e] = 0ull;
     }
+    // ---- warp 5: TMA producer.  One stage = one K tile (n_cols x 128 B) of one (column tile, digit plane) item.
+    // The first ring-full needs no free-slot wait: it is issued now, concurrently with the walk (the digit stream
+    // does not depend on the candidates).
+    const uint8_t* src_tiles = tiles + (size_t)sample * nt_n * PU_SLICES * kt_n * PU_B_TILE;
+    const int items = nt_n * PU_SLICES;
+    const int loads = items * kt_n;  // global tile index == load index: tiles are stored [nt][slice][kt]
+    const int last_cols = kt_n * PU_KB - (nt_n - 1) * PU_N;  // columns of the last column tile (128 or 256)
+    __syncthreads();  // barriers initialised
+    if (warp == 5 && lane == 0) {
+        for (int ld = 0; ld < nstages && ld < loads; ++ld) {
+            const int nt = ld / (PU_SLICES * kt_n);
+            const uint32_t bytes = (uint32_t)((nt == nt_n - 1) ? last_cols : PU_N) * PU_KB;
+            pu_mbar_expect_tx(full_bar + ld, bytes);
+            pu_bulk_g2s(ring + (size_t)ld * PU_B_TILE, src_tiles + (size_t)ld * PU_B_TILE, bytes, full_bar + ld);
+        }
+    }
+
+    // ---- walk: PU_WALK_GROUPS threads per candidate (group g takes the trees t = g mod groups): leaf columns into
+    // the row's bit mask, partial means per group
+    {
+        const int wg = (warp < 4) ? 0 : (warp >= 6 ? 1 + (warp - 6) / 4 : -1);
+        const int row = (warp < 4) ? tid : (warp >= 6 ? (tid - 6 * 32) % PU_ROWS : 0);
+        if (wg >= 0) {
+            double mean = 0.0;
+            if (row < np) {
+                const double* xp = xs + row;
+                for (int t = wg; t < m; t += PU_WALK_GROUPS) {
+                    const WalkNode* wn = tb + (size_t)t * hi;
+                    WalkNode nd = wn[0];
+                    for (int it = 0; it < hi && !(nd.feat_leaf & 0x8000u); ++it) {
+                        const int f = nd.feat_leaf & 0x7fffu;
+                        const uint32_t at = goes_left(xp[(size_t)f * (PU_ROWS + 1)], nd.thr, ftc[f]) ? nd.left : nd.right;
+                        nd = wn[min(at, (uint32_t)(hi - 1))];
+                    }
+                    const int col = __float_as_int(nd.thr);
+                    mean += w_s[col];
+                    atomicOr(zmask + (size_t)(col >> 6) * PU_ROWS + row, 1ull << (col & 63));
+                }
+            }
+            meanp[wg * PU_ROWS + row] = mean;
+        }
+    }
+    __syncthreads();
+    // ---- one-hot A operand (K-major, SWIZZLE_128B) from the masks: one 16-byte chunk per thread and step
+    {
+        const int chunks_per_row = kt_n * 8;
+        for (int e = tid; e < PU_ROWS * chunks_per_row; e += PU_THREADS) {
+            const int row = e / chunks_per_row, ch = e % chunks_per_row;
+            const uint32_t bits = (uint32_t)(zmask[(size_t)(ch >> 2) * PU_ROWS + row] >> ((ch & 3) * 16)) & 0xFFFFu;
+            const uint32_t r = (uint32_t)row, c = (uint32_t)(ch & 7);
+            unsigned char* dst = a_tiles + (size_t)(ch >> 3) * PU_A_TILE + (r >> 3) * 1024u + (r & 7) * 128u + ((c ^ (r & 7)) << 4);
+            *reinterpret_cast<uint4*>(dst) = pu_expand16(bits);
+        }
+    }
+    asm volatile("fence.proxy.async;" ::: "memory");  // generic writes of the A operand -> tensor-core (async proxy) reads
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_d = *tmem_slot;
 
-    // ---- walk: one candidate per thread (warps 0-3); one-hot A operand, column masks, mean
-    double mean = 0.0;
-    if (warp < 4 && tid < np) {
-        const double* xp = xs + tid;
-        for (int t = 0; t < m; ++t) {
-            const WalkNode* wn = tb + (size_t)t * hi;
-            WalkNode nd = wn[0];
-            for (int it = 0; it < hi && !(nd.feat_leaf & 0x8000u); ++it) {
-                const int f = nd.feat_leaf & 0x7fffu;
-                const uint32_t at = goes_left(xp[(size_t)f * (PU_ROWS + 1)], nd.thr, ftc[f]) ? nd.left : nd.right;
-                nd = wn[min(at, (uint32_t)(hi - 1))];
-            }
-            const int col = __float_as_int(nd.thr);
-            mean += w_s[col];
-            a_tiles[(size_t)(col >> 7) * PU_A_TILE + pu_swizzle((uint32_t)tid, (uint32_t)(col & 127))] = 1;
-            zmask[(size_t)tid * nt_n + (col >> 6)] |= 1ull << (col & 63);
-        }
-    }
-    // ---- warp 5: TMA producer.  One item = all K tiles of one (column tile nt, digit plane): a single bulk copy.
-    // It starts before the walk is finished (the digit stream does not depend on the candidates).
-    const uint8_t* src = tiles + (size_t)sample * nt_n * PU_SLICES * kt_n * PU_B_TILE;
-    const int items = nt_n * PU_SLICES;
-    if (warp == 5 && lane == 0) {
-        // the first ring-full of items needs no free-slot wait: issue it now, concurrently with the walk
-        for (int it = 0; it < nstages && it < items; ++it) {
-            pu_mbar_expect_tx(full_bar + it, stage_bytes);
-            pu_bulk_g2s(ring + (size_t)it * stage_bytes, src + (size_t)it * stage_bytes, stage_bytes, full_bar + it);
-        }
-    }
-    asm volatile("fence.proxy.async;" ::: "memory");  // generic writes of the A operand -> tensor-core (async proxy) reads
-    __syncthreads();
-    if (warp == 5 && lane == 0) {
-        for (int it = nstages; it < items; ++it) {
-            const int s = it % nstages;
-            pu_mbar_wait(empty_bar + s, (uint32_t)((it / nstages - 1) & 1));
-            pu_mbar_expect_tx(full_bar + s, stage_bytes);
-            pu_bulk_g2s(ring + (size_t)s * stage_bytes, src + (size_t)it * stage_bytes, stage_bytes, full_bar + s);
-        }
-    }
-
-    if (warp == 4) {
+    if (warp == 5) {
         if (lane == 0) {
-            // ---- MMA issuer
-            const uint32_t idesc = pu_idesc_i8(PU_ROWS, PU_N);
+            for (int ld = nstages; ld < loads; ++ld) {
+                const int s = ld % nstages;
+                const int nt = ld / (PU_SLICES * kt_n);
+                const uint32_t bytes = (uint32_t)((nt == nt_n - 1) ? last_cols : PU_N) * PU_KB;
+                pu_mbar_wait(empty_bar + s, (uint32_t)((ld / nstages - 1) & 1));
+                pu_mbar_expect_tx(full_bar + s, bytes);
+                pu_bulk_g2s(ring + (size_t)s * PU_B_TILE, src_tiles + (size_t)ld * PU_B_TILE, bytes, full_bar + s);
+            }
+        }
+        __syncwarp();
+    } else if (warp == 4) {
+        if (lane == 0) {
+            // ---- MMA issuer: item = (column tile, digit plane) into TMEM buffer item & 1
+            int ld = 0;
             for (int it = 0; it < items; ++it) {
-                const int nt = it / PU_SLICES, slice = it % PU_SLICES;
-                if (slice == 0 && nt > 0) pu_mbar_wait(acc_free, (uint32_t)((nt - 1) & 1));  // epilogue has drained TMEM
-                const int s = it % nstages;
-                pu_mbar_wait(full_bar + s, (uint32_t)((it / nstages) & 1));
+                const int nt = it / PU_SLICES, buf = it & 1, use = it >> 1;
+                const int ncols = (nt == nt_n - 1) ? last_cols : PU_N;
+                const uint32_t idesc = pu_idesc_i8(PU_ROWS, ncols);
+                if (use > 0) pu_mbar_wait(acc_free + buf, (uint32_t)((use - 1) & 1));  // epilogue has drained the buffer
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                for (int kt = 0; kt < kt_n; ++kt) {
+                for (int kt = 0; kt < kt_n; ++kt, ++ld) {
+                    const int s = ld % nstages;
+                    pu_mbar_wait(full_bar + s, (uint32_t)((ld / nstages) & 1));
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t a_addr = pu_smem(a_tiles + (size_t)kt * PU_A_TILE);
-                    const uint32_t b_addr = pu_smem(ring + (size_t)s * stage_bytes + (size_t)kt * PU_B_TILE);
+                    const uint32_t b_addr = pu_smem(ring + (size_t)s * PU_B_TILE);
 #pragma unroll
                     for (int k4 = 0; k4 < PU_KB / 32; ++k4)
-                        pu_umma_i8(tmem_d + (uint32_t)(slice * PU_N), pu_desc_sw128(a_addr + k4 * 32),
+                        pu_umma_i8(tmem_d + (uint32_t)(buf * PU_N), pu_desc_sw128(a_addr + k4 * 32),
                                    pu_desc_sw128(b_addr + k4 * 32), idesc, (kt > 0 || k4 > 0) ? 1u : 0u);
+                    pu_commit(empty_bar + s);
                 }
-                pu_commit(empty_bar + s);
-                if (slice == PU_SLICES - 1) pu_commit(acc_full);
+                pu_commit(acc_full + buf);
             }
         }
         __syncwarp();
@@ -302,35 +345,41 @@ predict_umma_kernel(WsLayout lay, const void* ws, const WalkNode* __restrict__ t
         int acc[PU_SLICES];
 #pragma unroll
         for (int s = 0; s < PU_SLICES; ++s) acc[s] = 0;
+        int it = 0;
         for (int nt = 0; nt < nt_n; ++nt) {
-            pu_mbar_wait(acc_full, (uint32_t)(nt & 1));
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const unsigned long long zm = zmask[(size_t)tid * nt_n + nt];
-            if (__any_sync(0xffffffffu, zm != 0ull)) {
+            const int ncols = (nt == nt_n - 1) ? last_cols : PU_N;
+            unsigned long long zm[PU_N / 64];
 #pragma unroll
-                for (int half = 0; half < 2; ++half) {
-                    const uint32_t bits = (uint32_t)(zm >> (32 * half));
+            for (int q = 0; q < PU_N / 64; ++q) zm[q] = (q * 64 < ncols) ? zmask[(size_t)(nt * (PU_N / 64) + q) * PU_ROWS + tid] : 0ull;
+#pragma unroll
+            for (int s = 0; s < PU_SLICES; ++s, ++it) {
+                const int buf = it & 1, use = it >> 1;
+                pu_mbar_wait(acc_full + buf, (uint32_t)(use & 1));
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                int a = acc[s];
+#pragma unroll
+                for (int j = 0; j < PU_N / 32; ++j) {
+                    const uint32_t bits = (uint32_t)(zm[j >> 1] >> (32 * (j & 1)));
                     if (__any_sync(0xffffffffu, bits != 0u)) {
+                        uint32_t v[32];
+                        pu_tmem_ld32(tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * PU_N + 32 * j), v);
 #pragma unroll
-                        for (int s = 0; s < PU_SLICES; ++s) {
-                            uint32_t v[32];
-                            pu_tmem_ld32(tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)(s * PU_N + 32 * half), v);
-                            int a = acc[s];
-#pragma unroll
-                            for (int j = 0; j < 32; ++j) a += (int)v[j] * (int)((bits >> j) & 1u);
-                            acc[s] = a;
-                        }
+                        for (int c = 0; c < 32; ++c) a += (int)v[c] * (int)((bits >> c) & 1u);
                     }
                 }
+                acc[s] = a;
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                pu_mbar_arrive(acc_free + buf);
             }
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            pu_mbar_arrive(acc_free);
         }
         if (tid < np) {
             // z^T Binv z = 2^-shift * sum_k 256^k acc_k   (each acc_k exact)
             double tsum = 0.0;
 #pragma unroll
             for (int s = PU_SLICES - 1; s >= 0; --s) tsum = tsum * 256.0 + (double)acc[s];
+            double mean = 0.0;
+#pragma unroll
+            for (int g = 0; g < PU_WALK_GROUPS; ++g) mean += meanp[g * PU_ROWS + tid];
             const int64_t o = sample * n_c + p0 + tid;
             mu[o] = mean;
             var[o] = cv.sc->sig * (tsum * scales[sample]);
@@ -379,11 +428,11 @@ int bark_predict_umma(const bark_mcmc_dims* dims, const void* workspace, const v
     BARK_CHECK_ARG(dims->chains <= 65535, "too many samples per call");
     const WsLayout lay = make_layout(*dims);
     const PrepLayout pl = prep_layout(dims->chains, dims->m, slots, p_max);
-    const int stage_bytes = pl.kt * PU_B_TILE;
-    const size_t fixed = pu_smem_layout((int)lay.m, slots, (int)lay.d, pl.kt, pl.nt, 0).total;
+    const int stage_bytes = PU_B_TILE;
+    const size_t fixed = pu_smem_layout((int)lay.m, slots, (int)lay.d, pl.kt, 0).total;
     BARK_CHECK_ARG(fixed + 2 * (size_t)stage_bytes <= 227 * 1024, "m * slots / d / p_max too large for the predict kernel's shared memory");
     const int ring_bytes = (int)(std::min<size_t>(PU_RING_MAX, 227 * 1024 - fixed) / stage_bytes) * stage_bytes;
-    const PuSmem sl = pu_smem_layout((int)lay.m, slots, (int)lay.d, pl.kt, pl.nt, ring_bytes);
+    const PuSmem sl = pu_smem_layout((int)lay.m, slots, (int)lay.d, pl.kt, ring_bytes);
     BARK_CUDA(cudaFuncSetAttribute(predict_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sl.total));
     const unsigned char* base = (const unsigned char*)prep;
     dim3 grid((unsigned)ceil_div(n_c, PU_ROWS), (unsigned)dims->chains);

@@ -27,10 +27,10 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 # dram__bytes_read.sum + dram__bytes_write.sum of sweep_trees_kernel, one `ncu --set full` capture of this workload
-# (profiles/r1_b_ncu_full_summary.csv): the leaf-space state is L2-resident (86 % L2 hit rate), so DRAM traffic is
+# (profiles/r1_c_ncu_full_summary.csv): the leaf-space state is L2-resident (86 % L2 hit rate), so DRAM traffic is
 # far below the algorithmic bytes.
-NCU_DRAM_BYTES_PER_LAUNCH = 1.97e9
-NCU_SOURCE = "profiles/r1_b_ncu_full_summary.csv (ncu --set full, round 1)"
+NCU_DRAM_BYTES_PER_LAUNCH = 2.218e9
+NCU_SOURCE = "profiles/r1_c_ncu_full_summary.csv (ncu --set full, round 1)"
 
 METRIC = "mcmc_proposals_per_sec_full_mll"
 UNIT = "proposals/s"
@@ -48,6 +48,8 @@ def parse_args():
     ap.add_argument("--chains-per-gpu", type=int, default=64)
     ap.add_argument("--burnin", type=int, default=120, help="untimed sweeps that bring the chains to posterior-sized forests")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--predict-candidates", type=int, default=1 << 21,
+                    help="candidates of the predict figure in `extras` (default: BASELINE config 5's per-GPU shard, 2 Mi)")
     ap.add_argument("--cpu-budget-s", type=float, default=25.0, help="target CPU seconds of the bounded baseline sample")
     return ap.parse_args()
 
@@ -309,7 +311,7 @@ def run_b200_arm(a, rank, local_rank, world):
         hf_all = st.dforest.to_numpy()
         rr = st.read()
         ps = B.PosteriorState((hf_all, rr["noise"].cpu().numpy(), rr["scale"].cpu().numpy()), (X, y), ft, a.d, device=dev)
-        n_c = 32768
+        n_c = a.predict_candidates  # BASELINE config 5: 16 Mi candidates over 8 GPUs = 2 Mi per GPU, x 64 samples
         cand = torch.rand((n_c, a.d), dtype=torch.float64, device=dev)
         ps.predict_device(cand, mode=1)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
