@@ -26,8 +26,8 @@ constexpr int PU_N = 256;           // Binv columns per accumulator tile (UMMA N
 constexpr int PU_KB = 128;          // K bytes per operand tile (one SWIZZLE_128B atom row)
 constexpr int PU_SLICES = 7;        // base-256 digit planes
 constexpr int PU_MAX_STAGES = 4;    // ring stages; one stage = one K tile of one (column tile, digit plane)
-constexpr int PU_WALK_GROUPS = 3;   // threads per candidate in the walk (trees t = g mod 3)
-constexpr int PU_THREADS = 448;     // warps 0-3: walk + epilogue, 4: MMA issue, 5: TMA producer, 6-13: walk
+constexpr int PU_WALK_GROUPS = 4;   // threads per candidate: walk (trees t = g mod 4) and epilogue (column chunks j = g mod 4)
+constexpr int PU_THREADS = 576;     // warps 0-3 and 6-17: walk + epilogue groups, 4: MMA issue, 5: TMA producer
 constexpr int PU_A_TILE = PU_ROWS * PU_KB;  // 16 KB
 constexpr int PU_B_TILE = PU_N * PU_KB;     // 32 KB
 constexpr int PU_RING_MAX = 128 * 1024;
@@ -164,7 +164,7 @@ __device__ __forceinline__ void pu_tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) 
 }
 
 struct PuSmem {
-    size_t off_a, off_ring, off_table, off_zmask, off_w, off_xs, off_ft, off_mean, off_bars, total;
+    size_t off_a, off_ring, off_table, off_zmask, off_w, off_xs, off_ft, off_mean, off_part, off_bars, total;
 };
 __host__ __device__ inline PuSmem pu_smem_layout(int m, int hi, int d, int kt, int ring_bytes) {
     PuSmem s;
@@ -177,6 +177,7 @@ __host__ __device__ inline PuSmem pu_smem_layout(int m, int hi, int d, int kt, i
     s.off_xs = o;     o = align256(o + (size_t)d * (PU_ROWS + 1) * 8);
     s.off_ft = o;     o = align256(o + (size_t)d * 4);
     s.off_mean = o;   o = align256(o + (size_t)PU_WALK_GROUPS * PU_ROWS * 8);
+    s.off_part = o;   o = align256(o + (size_t)(PU_WALK_GROUPS - 1) * PU_SLICES * PU_ROWS * 4);
     s.off_bars = o;   o = align256(o + (size_t)(2 * PU_MAX_STAGES + 4) * 8 + 16);
     s.total = o;
     return s;
@@ -208,6 +209,7 @@ predict_umma_kernel(WsLayout lay, const void* ws, const WalkNode* __restrict__ t
     double* xs = reinterpret_cast<double*>(smem_raw + sl.off_xs);  // [d][PU_ROWS + 1]
     int* ftc = reinterpret_cast<int*>(smem_raw + sl.off_ft);
     double* meanp = reinterpret_cast<double*>(smem_raw + sl.off_mean);  // [group][row]
+    int* accp = reinterpret_cast<int*>(smem_raw + sl.off_part);          // [group - 1][slice][row]
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_raw + sl.off_bars);
     uint64_t* empty_bar = full_bar + PU_MAX_STAGES;
     uint64_t* acc_full = empty_bar + PU_MAX_STAGES;  // [2]
@@ -226,7 +228,7 @@ predict_umma_kernel(WsLayout lay, const void* ws, const WalkNode* __restrict__ t
     // ---- setup: barriers, TMEM, staging of the sample's trees / w and of the candidate tile
     if (tid == 0) {
         for (int s = 0; s < PU_MAX_STAGES; ++s) { pu_mbar_init(full_bar + s, 1); pu_mbar_init(empty_bar + s, 1); }
-        for (int b = 0; b < 2; ++b) { pu_mbar_init(acc_full + b, 1); pu_mbar_init(acc_free + b, PU_ROWS); }
+        for (int b = 0; b < 2; ++b) { pu_mbar_init(acc_full + b, 1); pu_mbar_init(acc_free + b, PU_ROWS * PU_WALK_GROUPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 4) {
@@ -261,8 +263,8 @@ predict_umma_kernel(WsLayout lay, const void* ws, const WalkNode* __restrict__ t
 
     // ---- walk: PU_WALK_GROUPS threads per candidate (group g takes the trees t = g mod groups): leaf columns into
     // the row's bit mask, partial means per group
+    const int wg = (warp < 4) ? 0 : (warp >= 6 ? 1 + (warp - 6) / 4 : -1);  // walk / epilogue group of this warp
     {
-        const int wg = (warp < 4) ? 0 : (warp >= 6 ? 1 + (warp - 6) / 4 : -1);
         const int row = (warp < 4) ? tid : (warp >= 6 ? (tid - 6 * 32) % PU_ROWS : 0);
         if (wg >= 0) {
             double mean = 0.0;
@@ -340,8 +342,10 @@ predict_umma_kernel(WsLayout lay, const void* ws, const WalkNode* __restrict__ t
             }
         }
         __syncwarp();
-    } else if (warp < 4) {
-        // ---- epilogue (thread = candidate row): masked int32 row sums of every digit plane
+    } else {
+        // ---- epilogue: masked int32 row sums of every digit plane.  A warp reads the TMEM lanes of its quarter
+        // (warp % 4), thread = candidate row; the four groups share the 32-column chunks of every item.
+        const int row = 32 * (warp & 3) + lane;
         int acc[PU_SLICES];
 #pragma unroll
         for (int s = 0; s < PU_SLICES; ++s) acc[s] = 0;
@@ -350,7 +354,7 @@ predict_umma_kernel(WsLayout lay, const void* ws, const WalkNode* __restrict__ t
             const int ncols = (nt == nt_n - 1) ? last_cols : PU_N;
             unsigned long long zm[PU_N / 64];
 #pragma unroll
-            for (int q = 0; q < PU_N / 64; ++q) zm[q] = (q * 64 < ncols) ? zmask[(size_t)(nt * (PU_N / 64) + q) * PU_ROWS + tid] : 0ull;
+            for (int q = 0; q < PU_N / 64; ++q) zm[q] = (q * 64 < ncols) ? zmask[(size_t)(nt * (PU_N / 64) + q) * PU_ROWS + row] : 0ull;
 #pragma unroll
             for (int s = 0; s < PU_SLICES; ++s, ++it) {
                 const int buf = it & 1, use = it >> 1;
@@ -359,10 +363,11 @@ predict_umma_kernel(WsLayout lay, const void* ws, const WalkNode* __restrict__ t
                 int a = acc[s];
 #pragma unroll
                 for (int j = 0; j < PU_N / 32; ++j) {
+                    if ((j & (PU_WALK_GROUPS - 1)) != wg) continue;  // warp-uniform
                     const uint32_t bits = (uint32_t)(zm[j >> 1] >> (32 * (j & 1)));
                     if (__any_sync(0xffffffffu, bits != 0u)) {
                         uint32_t v[32];
-                        pu_tmem_ld32(tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * PU_N + 32 * j), v);
+                        pu_tmem_ld32(tmem_d + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(buf * PU_N + 32 * j), v);
 #pragma unroll
                         for (int c = 0; c < 32; ++c) a += (int)v[c] * (int)((bits >> c) & 1u);
                     }
@@ -372,15 +377,25 @@ predict_umma_kernel(WsLayout lay, const void* ws, const WalkNode* __restrict__ t
                 pu_mbar_arrive(acc_free + buf);
             }
         }
-        if (tid < np) {
+        if (wg > 0) {
+#pragma unroll
+            for (int s = 0; s < PU_SLICES; ++s) accp[((wg - 1) * PU_SLICES + s) * PU_ROWS + row] = acc[s];
+        }
+        asm volatile("bar.sync 1, %0;" ::"r"(PU_WALK_GROUPS * PU_ROWS) : "memory");  // the epilogue warps only
+        if (wg == 0 && row < np) {
             // z^T Binv z = 2^-shift * sum_k 256^k acc_k   (each acc_k exact)
             double tsum = 0.0;
 #pragma unroll
-            for (int s = PU_SLICES - 1; s >= 0; --s) tsum = tsum * 256.0 + (double)acc[s];
+            for (int s = PU_SLICES - 1; s >= 0; --s) {
+                int a = acc[s];
+#pragma unroll
+                for (int g = 1; g < PU_WALK_GROUPS; ++g) a += accp[((g - 1) * PU_SLICES + s) * PU_ROWS + row];
+                tsum = tsum * 256.0 + (double)a;
+            }
             double mean = 0.0;
 #pragma unroll
-            for (int g = 0; g < PU_WALK_GROUPS; ++g) mean += meanp[g * PU_ROWS + tid];
-            const int64_t o = sample * n_c + p0 + tid;
+            for (int g = 0; g < PU_WALK_GROUPS; ++g) mean += meanp[g * PU_ROWS + row];
+            const int64_t o = sample * n_c + p0 + row;
             mu[o] = mean;
             var[o] = cv.sc->sig * (tsum * scales[sample]);
         }
