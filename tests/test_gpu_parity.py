@@ -405,3 +405,93 @@ def test_sampler_ragged_sizes():
         want, trace_o, got, _ = replay_case(n=n, dim=dim, cat=0, m=m, chains=chains, warm=6, ns=1, sps=4, seed=n)
         assert got[0].tobytes() == want[0].tobytes()
         assert np.allclose(got[1], want[1], rtol=1e-12, atol=0)
+
+
+# ------------------------------------------------------------ full-size properties (BASELINE config 4 shape)
+def test_full_size_state_properties():
+    """N=2000, m=200 (BASELINE config 4's shape, 4 of the 64 chains): after free-running sweeps the leaf-space state
+    is exactly the one of the final forest (integer parts bit-exact), B^-1 is an inverse, and the running log-MLL
+    equals both the GPU from-scratch evaluation and the oracle's dense Cholesky value to 1e-9."""
+    n, m, chains = 2000, 200, 4
+    X, y, bounds, ft, _ = O.synthetic_problem(n, dim=10, cat_dim=0, m_true=50, seed=0)
+    f0 = np.tile(O.create_empty_forest(m), (chains, 1, 1))
+    st = S.ChainState(f0, np.full(chains, 0.1), np.full(chains, 1.0), X, y, bounds, ft)
+    p = B.BARKTrainParams(num_chains=chains)
+    st.sweeps(p, 60, seed=11)
+    r = st.read()
+    assert int(r["status"].max()) == 0
+    forest = st.dforest.to_numpy()
+    noise, scale, run = r["noise"].cpu().numpy(), r["scale"].cpu().numpy(), r["mll"].cpu().numpy()
+    scratch = B.forest_mll(forest, noise, scale, X, y, ft)
+    assert np.abs(run - scratch).max() / np.abs(scratch).max() < 1e-9
+    leaves_gpu = B.pass_through_forest(forest, X, ft)
+    for c in (0, chains - 1):
+        ex = st.export(c)
+        leaves = O.pass_through_forest(forest[c], X, ft)
+        assert np.array_equal(leaves_gpu[c], leaves)
+        cm, P = ex["colmap"], st.p_cap
+        cols = np.stack([cm[t, leaves[:, t]] for t in range(m)], axis=1)  # (n, m) leaf-space column of every point
+        assert cols.min() >= 0
+        Z = np.zeros((n, P))
+        Z[np.arange(n)[:, None], cols] = 1
+        A = (Z.T @ Z).astype(np.int32)
+        assert np.array_equal(ex["A"], A)
+        cc = (noise[c] + 1e-6) * m / scale[c]
+        assert np.abs(ex["Binv"] @ (cc * np.eye(P) + A) - np.eye(P)).max() < 1e-7
+        K = O.kernel_matrix(forest[c], X, ft, noise[c], scale[c])
+        assert run[c] == pytest.approx(O.mll_cholesky(K, y), rel=1e-9)
+        assert int(r["p_used"][c]) == int((forest[c]["active"] & forest[c]["is_leaf"]).sum())
+
+
+def test_full_size_predict_properties():
+    """Posterior predict at config-4/5 shape: both GPU kernels agree, the variance is positive and below the prior
+    variance, the mixture moments equal the host formula, and a sub-sample of candidates matches the oracle."""
+    n, m, chains = 2000, 200, 4
+    X, y, bounds, ft, _ = O.synthetic_problem(n, dim=10, cat_dim=0, m_true=50, seed=0)
+    f0 = np.tile(O.create_empty_forest(m), (chains, 1, 1))
+    p = B.BARKTrainParams(warmup_steps=40, num_samples=2, steps_per_sample=5, num_chains=chains)
+    ns, noise, scale = B.run_bark_sampler((f0, np.full(chains, 0.1), np.full(chains, 1.0)), (X, y), (bounds, ft), p, seed=5)
+    rng = np.random.default_rng(0)
+    cand = rng.random((4099, 10))  # ragged: not a multiple of the 128-candidate tile
+    import torch
+    ps = B.PosteriorState((ns, noise, scale), (X, y), ft, 10)
+    ps_ref = B.PosteriorState((ns, noise, scale), (X, y), ft, 10, tensor_cores=False)
+    cd = torch.tensor(cand, device="cuda")
+    mu, var = (t.cpu().numpy() for t in ps.predict_device(cd, mode=0))
+    mu2, var2 = (t.cpu().numpy() for t in ps_ref.predict_device(cd, mode=0))
+    assert mu.shape == (chains * 2, 4099)
+    assert np.allclose(mu, mu2, rtol=1e-12, atol=1e-12) and np.allclose(var, var2, rtol=1e-9, atol=1e-12)
+    assert (var > 0).all() and (var <= (scale.reshape(-1) + 1e-9)[:, None]).all()
+    mmu, mvar = (t.cpu().numpy() for t in ps.predict_device(cd, mode=1))
+    hmu, hvar = B.mixture_of_gaussians_as_normal(mu, var)
+    assert np.allclose(mmu, hmu, rtol=1e-12, atol=1e-12) and np.allclose(mvar, hvar, rtol=1e-9, atol=1e-12)
+    sub = cand[:48]
+    omu, ovar = O.forest_predict((ns[:1], noise[:1], scale[:1]), (X, y.reshape(-1, 1)), sub, ft)
+    assert np.allclose(mu[:2, :48], omu, rtol=1e-9, atol=1e-9)
+    assert np.allclose(var[:2, :48], ovar, rtol=1e-7, atol=1e-9)
+
+
+# ------------------------------------------------------------ stochastic layer (SURVEY 8c parity protocol)
+def test_posterior_statistics_match_oracle_sampler():
+    """Free-running GPU chains (Philox) and free-running oracle chains (numba RNG) target the same posterior:
+    chain-averaged noise, leaves per tree, and acceptance rate agree within Monte-Carlo error (BASELINE config 1
+    shape: N=50, m=50, TreeFunction data; 48 chains each)."""
+    n, m, chains = 50, 50, 48
+    X, y, bounds, ft, _ = O.synthetic_problem(n, dim=5, cat_dim=0, m_true=50, seed=3)
+    p = B.BARKTrainParams(warmup_steps=60, num_samples=8, steps_per_sample=5, num_chains=chains)
+    f0 = np.tile(O.create_empty_forest(m), (chains, 1, 1))
+    model = (f0, np.full(chains, 0.1), np.full(chains, 1.0))
+    ns_g, no_g, _, info = B.run_bark_sampler(model, (X, y), (bounds, ft), p, seed=2024, return_info=True)
+    O.seed_numba(99)
+    ns_o, no_o, _ = O.run_bark_sampler((f0.copy(), model[1].copy(), model[2].copy()), (X, y), bounds, ft, p)
+
+    def per_chain(ns, no):
+        leaves = (ns["active"] & ns["is_leaf"]).sum(axis=-1).mean(axis=(1, 2))  # mean leaves per tree, per chain
+        depth = np.where(ns["active"] & ns["is_leaf"], ns["depth"], 0).max(axis=-1).mean(axis=(1, 2))
+        return np.log(no).mean(axis=1), leaves, depth
+
+    for a, b, name in zip(per_chain(ns_g, no_g), per_chain(ns_o, no_o), ("log noise", "leaves/tree", "max depth")):
+        se = np.sqrt(a.var(ddof=1) / chains + b.var(ddof=1) / chains)
+        assert abs(a.mean() - b.mean()) < 4.5 * se + 1e-3, (name, a.mean(), b.mean(), se)
+    acc = info["accepted"].sum() / info["tree_proposals"].sum()
+    assert 0.05 < acc < 0.9
