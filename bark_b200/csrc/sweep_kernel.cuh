@@ -825,45 +825,32 @@ sweep_trees_kernel(WsLayout lay, void* ws, bark_nodes_soa forest, bark_params pr
                         const uint32_t use = ring_base + (uint32_t)j;
                         const int slot = (int)(use % (uint32_t)nslot);
                         mbar_wait(full_bar + slot, (use / (uint32_t)nslot) & 1u, &sc->status);
-                        double* rowA = reinterpret_cast<double*>(ring + (size_t)slot * slot_bytes);
-                        double* rowB = rowA + lenA;
+                        const double* rowA = reinterpret_cast<const double*>(ring + (size_t)slot * slot_bytes);
+                        const double* rowB = rowA + lenA;
+                        double* gA = cv.Binv + (size_t)qA * P;
+                        double* gB = cv.Binv + (size_t)qB * P;
+                        // updated rows go straight from registers to global memory (L2): the slot is free as soon as
+                        // it has been read, and the store traffic does not queue behind the bulk loads
                         for (int kk = lane * 2; kk < lenB || kk < lenA; kk += 64) {
                             const double2 dd = *reinterpret_cast<const double2*>(Wd + kk);
                             const double2 vv = *reinterpret_cast<const double2*>(Wv + kk);
                             if (kk < lenA) {
-                                double2 x = *reinterpret_cast<double2*>(rowA + kk);
+                                double2 x = *reinterpret_cast<const double2*>(rowA + kk);
                                 x.x -= adA * dd.x + avA * vv.x;
                                 x.y -= adA * dd.y + avA * vv.y;
-                                *reinterpret_cast<double2*>(rowA + kk) = x;
+                                __stcg(reinterpret_cast<double2*>(gA + kk), x);
                             }
                             if (kk < lenB) {
-                                double2 x = *reinterpret_cast<double2*>(rowB + kk);
+                                double2 x = *reinterpret_cast<const double2*>(rowB + kk);
                                 x.x -= adB * dd.x + avB * vv.x;
                                 x.y -= adB * dd.y + avB * vv.y;
-                                *reinterpret_cast<double2*>(rowB + kk) = x;
+                                __stcg(reinterpret_cast<double2*>(gB + kk), x);
                             }
                         }
-                        fence_proxy_async();  // generic-proxy writes to the slot -> bulk store (async proxy) reads
                         __syncwarp();
-                        if (lane == 0) {
-                            bulk_s2g(cv.Binv + (size_t)qA * P, rowA, (uint32_t)lenA * 8u);
-                            if (hasB) bulk_s2g(cv.Binv + (size_t)qB * P, rowB, (uint32_t)lenB * 8u);
-                            bulk_commit();
-                            if (prev_slot >= 0) {
-                                bulk_wait_read1();
-                                mbar_arrive(empty_bar + prev_slot);
-                            }
-                        }
-                        prev_slot = slot;
+                        if (lane == 0) mbar_arrive(empty_bar + slot);
                     }
-                    if (lane == 0) {
-                        if (prev_slot >= 0) {
-                            bulk_wait_read0();
-                            mbar_arrive(empty_bar + prev_slot);
-                        }
-                        bulk_wait0();  // this warp's row stores are complete
-                        fence_proxy_async();
-                    }
+                    fence_proxy_async();  // generic stores of the rows -> later bulk loads (async proxy)
                 }
                 ring_base += (uint32_t)npairs;
             } else {
