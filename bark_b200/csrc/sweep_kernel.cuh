@@ -28,7 +28,7 @@ namespace cg = cooperative_groups;
 
 constexpr int SW_THREADS = 512;
 constexpr int SW_WARPS = SW_THREADS / 32;
-constexpr int SW_MAX_R = 2;
+constexpr int SW_MAX_R = 4;  // CTAs per chain: 1, 2 or 4 (the used extent is a multiple of 16, so every share is a multiple of 4)
 constexpr int SW_PROD_WARP = SW_WARPS - 1;  // bulk-copy producer
 constexpr int SW_NCW = SW_WARPS - 1;        // consumer warps
 constexpr int SW_NSLOT_MAX = 60;  // multiple of SW_NCW
@@ -695,7 +695,9 @@ sweep_trees_kernel(WsLayout lay, void* ws, bark_nodes_soa forest, bark_params pr
             if (p.move != MOVE_PRUNE) {
                 for (int k = tid; k < pe16; k += SW_THREADS) {
                     double sacc = parts[k];
-                    if (R > 1) sacc += parts[parts_stride + k];
+#pragma unroll
+                    for (int r = 1; r < SW_MAX_R; ++r)
+                        if (r < R) sacc += parts[r * parts_stride + k];
                     Wv[k] = sacc;
                 }
                 __syncthreads();
