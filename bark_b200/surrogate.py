@@ -103,3 +103,42 @@ class BARKSurrogate:
                                         add_noise=predict_observed)
             mu, var = mu.cpu().numpy(), var.cpu().numpy()
         return mu[..., np.newaxis], np.sqrt(var[..., np.newaxis])
+
+
+    # ---- on-disk samples (the reference's _dumps / loads are stubs, surrogates/bark.py:96-100)
+    def save(self, path) -> None:
+        from .checkpoint import save_samples
+        save_samples(path, self.model_as_tuple(), self.train_data, self.bark_params,
+                     extra={"scaler_mean": float(self.scaler.mean), "scaler_std": float(self.scaler.std), "fits": self._fits})
+
+    def load(self, path):
+        from .checkpoint import load_samples
+        ck = load_samples(path)
+        self.forest, self.noise, self.scale = ck["model"]
+        self.train_data = ck["data"]
+        self.scaler.mean, self.scaler.std = ck["extra"].get("scaler_mean", 0.0), ck["extra"].get("scaler_std", 1.0)
+        self._fits = int(ck["extra"].get("fits", 1))
+        self._posterior = None
+        return self
+
+
+class BARKPriorSurrogate(BARKSurrogate):
+    """Samples from the BARK prior instead of the posterior (src/bofire_mixed/surrogates/bark.py:152-189):
+    `fit` only stores the training data and draws `num_samples` prior forests / noise values; `predict` is the
+    same GPU path as for posterior samples."""
+
+    def __init__(self, domain, *, num_samples=5, sample_seed=None, **kwargs):
+        super().__init__(domain, num_samples=num_samples, **kwargs)
+        self.sample_rng = np.random.default_rng(sample_seed)
+
+    def fit(self, X: np.ndarray, Y: np.ndarray):
+        from .prior import sample_forest_prior, sample_noise_prior
+        Y = np.asarray(Y, dtype=np.float64).reshape(-1, 1)
+        self.train_data = (np.ascontiguousarray(X, dtype=np.float64), self.scaler(Y, train=True))
+        bounds, feat_types = unpack_domain(self.domain)
+        self.forest = sample_forest_prior(self.num_trees, bounds, feat_types, self.alpha, self.beta, self.num_samples,
+                                          self.sample_rng)
+        self.noise = sample_noise_prior(self.gamma_prior_shape, self.gamma_prior_rate, self.num_samples, self.sample_rng)
+        self.scale = np.ones((self.num_samples,))
+        self._posterior = None
+        return self

@@ -495,3 +495,29 @@ def test_posterior_statistics_match_oracle_sampler():
         assert abs(a.mean() - b.mean()) < 4.5 * se + 1e-3, (name, a.mean(), b.mean(), se)
     acc = info["accepted"].sum() / info["tree_proposals"].sum()
     assert 0.05 < acc < 0.9
+
+
+# ------------------------------------------------------------ prior surrogate, checkpoint / resume
+def test_prior_surrogate_and_checkpoint_resume(tmp_path):
+    X, y, bounds, ft, _ = O.synthetic_problem(70, dim=3, cat_dim=1, num_cat=4, m_true=10, seed=4)
+    y_raw = y * 1.7 - 0.3
+    prior = B.BARKPriorSurrogate((bounds, ft), num_samples=4, num_trees=12, sample_seed=3)
+    prior.fit(X, y_raw)
+    assert prior.forest.shape == (4, 12, 100) and prior.noise.shape == (4,) and np.all(prior.scale == 1.0)
+    Xc = X[:9]
+    mu, sd = prior.predict(Xc)
+    sc = O.Standardize(); sc.mean, sc.std = prior.scaler.mean, prior.scaler.std
+    want_mu, want_sd = O.surrogate_predict(prior.model_as_tuple(), prior.train_data, Xc, ft, sc)
+    assert np.allclose(mu, want_mu, rtol=1e-9, atol=1e-10) and np.allclose(sd, want_sd, rtol=1e-8, atol=1e-10)
+    # posterior fit -> save -> load into a fresh surrogate -> identical predictions, and the fit resumes warm
+    sur = B.BARKSurrogate((bounds, ft), warmup_steps=10, num_samples=2, steps_per_sample=3, num_trees=12, num_chains=2, seed=1)
+    sur.fit(X, y_raw)
+    path = tmp_path / "fit.npz"
+    sur.save(path)
+    sur2 = B.BARKSurrogate((bounds, ft), warmup_steps=10, num_samples=2, steps_per_sample=3, num_trees=12, num_chains=2, seed=1)
+    sur2.load(path)
+    assert sur2.forest.tobytes() == sur.forest.tobytes() and sur2.is_fitted
+    a, b = sur.predict(Xc), sur2.predict(Xc)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    sur2.fit(X, y_raw)
+    assert sur2.bark_params.warmup_steps == 0 and sur2.forest.shape == (2, 2, 12, 100)

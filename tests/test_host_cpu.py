@@ -110,3 +110,62 @@ def test_mixture_moments_host():
     mu, var = rng.standard_normal((6, 9)), rng.random((6, 9))
     m, v = bark_b200.mixture_of_gaussians_as_normal(mu, var)
     assert np.allclose(m, mu.mean(0)) and np.allclose(v, (var + mu**2).mean(0) - mu.mean(0) ** 2)
+
+
+# ------------------------------------------------------------ checkpoint format, prior sampler (host code)
+def test_checkpoint_roundtrip(tmp_path):
+    rng = np.random.default_rng(0)
+    bounds = np.array([[0.0, 1.0], [0.0, 31.0], [2.0, 9.0]])
+    ft = np.array([2, 0, 1])
+    forest = bark_b200.sample_forest_prior(12, bounds, ft, 0.95, 2.0, 6, rng).reshape(2, 3, 12, 100)
+    noise, scale = rng.random((2, 3)), rng.random((2, 3))
+    X, y = rng.random((7, 3)), rng.random((7, 1))
+    params = bark_b200.BARKTrainParams(warmup_steps=3, num_samples=3, num_chains=2, alpha=0.9)
+    path = tmp_path / "samples.npz"
+    bark_b200.save_samples(path, (forest, noise, scale), (X, y), params, extra={"note": "x"})
+    ck = bark_b200.load_samples(path)
+    assert ck["model"][0].dtype == bark_b200.NODE_RECORD_DTYPE and ck["model"][0].shape == forest.shape
+    assert ck["model"][0].tobytes() == forest.tobytes()
+    assert np.array_equal(ck["model"][1], noise) and np.array_equal(ck["model"][2], scale)
+    assert np.array_equal(ck["data"][0], X) and np.array_equal(ck["data"][1], y)
+    assert ck["params"].alpha == 0.9 and ck["params"].num_chains == 2 and ck["extra"] == {"note": "x"}
+    assert np.allclose(ck["params"].proposal_weights, params.proposal_weights)
+    with pytest.raises(TypeError):
+        bark_b200.save_samples(path, (np.zeros((2, 3)), noise, scale))
+
+
+def test_prior_sampler_structure_and_depth_law():
+    """bark_prior_sampler.py:15-93: a node at depth d splits with probability alpha (1+d)^-beta; rules are drawn
+    inside the node's subspace; the subspace restatement agrees with the oracle's."""
+    from bark_b200 import prior
+    from oracle import bark_oracle as O
+    rng = np.random.default_rng(1)
+    bounds = np.array([[0.0, 1.0], [-2.0, 3.0], [0.0, 31.0], [2.0, 9.0]])
+    ft = np.array([2, 2, 0, 1])
+    forests = bark_b200.sample_forest_prior(200, bounds, ft, 0.95, 2.0, 4, rng)
+    assert forests.shape == (4, 200, 100) and forests.dtype == bark_b200.NODE_RECORD_DTYPE
+    n_split_root = 0
+    for tree in forests.reshape(-1, 100):
+        act = np.flatnonzero(tree["active"])
+        assert tree[0]["active"] and tree[0]["depth"] == 0
+        n_split_root += int(tree[0]["is_leaf"] == 0)
+        for i in act:
+            nd = tree[i]
+            sub = prior.get_node_subspace(tree, int(i), bounds, ft)
+            want = O.get_node_subspace(tree, int(i), bounds, ft.astype(np.int64))
+            assert np.array_equal(sub, want)
+            if not nd["is_leaf"]:
+                l, r, f = int(nd["left"]), int(nd["right"]), int(nd["feature_idx"])
+                assert tree[l]["active"] and tree[r]["active"] and tree[l]["parent"] == i and tree[r]["parent"] == i
+                assert tree[l]["depth"] == nd["depth"] + 1 == tree[r]["depth"]
+                if ft[f] == 0:
+                    assert 0 < int(nd["threshold"]) < int(sub[f, 1]) and int(nd["threshold"]) & ~int(sub[f, 1]) == 0
+                elif ft[f] == 1:
+                    assert sub[f, 0] <= nd["threshold"] < sub[f, 1]
+                else:
+                    assert np.float32(sub[f, 0]) <= nd["threshold"] <= np.float32(sub[f, 1])
+    # root split probability alpha = 0.95 (every root rule is valid here): binomial(800, 0.95), 5 sigma
+    assert abs(n_split_root / 800 - 0.95) < 5 * np.sqrt(0.95 * 0.05 / 800)
+    assert all(prior._next_power_of_2(x) == O.next_power_of_2(x) for x in range(0, 70))
+    noise = bark_b200.sample_noise_prior(1.5, 5.0, 20000, np.random.default_rng(2))
+    assert abs(noise.mean() - 1.5 / 5.0) < 0.01
