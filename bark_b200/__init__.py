@@ -10,6 +10,7 @@ from .forest import (NODE_RECORD_DTYPE, FeatureTypeEnum, batched_forest_gram_mat
 from .mll import forest_mll  # noqa: F401
 from .predict import BARKModel, PosteriorState, forest_predict, mixture_of_gaussians_as_normal  # noqa: F401
 from .sampler import BARKTrainParams, BARKTrainParamsNumba, ChainState, run_bark_sampler  # noqa: F401
+from .acquisition import gp_sample_inverses  # noqa: F401
 from .checkpoint import load_samples, save_samples  # noqa: F401
 from .prior import sample_forest_prior, sample_noise_prior  # noqa: F401
 from .surrogate import BARKPriorSurrogate, BARKSurrogate, Standardize  # noqa: F401

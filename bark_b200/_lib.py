@@ -51,6 +51,10 @@ SIGNATURES = {
     "bark_mcmc_workspace_bytes": (c_size_t, [C.POINTER(McmcDims)]),
     "bark_mcmc_init": (c_int, [C.POINTER(McmcDims), c_void_p, NodesSoA, c_void_p, c_void_p, c_void_p, c_void_p,
                                c_void_p, c_void_p, c_void_p]),
+    "bark_mcmc_init_ex": (c_int, [C.POINTER(McmcDims), c_void_p, NodesSoA, c_void_p, c_void_p, c_void_p, c_void_p,
+                                  c_void_p, c_void_p, c_int32, c_void_p]),
+    "bark_kinv_scratch_bytes": (c_size_t, [C.POINTER(McmcDims)]),
+    "bark_kinv_export": (c_int, [C.POINTER(McmcDims), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "bark_mcmc_sweeps": (c_int, [C.POINTER(McmcDims), c_void_p, NodesSoA, C.POINTER(Params), c_int64, c_uint64,
                                  c_int64, c_int64, c_void_p, c_void_p, c_void_p]),
     "bark_mcmc_sweeps_timed": (c_int, [C.POINTER(McmcDims), c_void_p, NodesSoA, C.POINTER(Params), c_int64, c_uint64,
@@ -69,6 +73,8 @@ SIGNATURES = {
     "bark_predict_mixture": (c_int, [C.POINTER(McmcDims), c_void_p, c_void_p, c_void_p, c_int64, c_double, c_double,
                                      c_int, c_void_p, c_void_p, c_void_p]),
 }
+
+INIT_SKIP_NULL = 1
 
 _lib = None
 

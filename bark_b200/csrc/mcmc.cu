@@ -83,7 +83,7 @@ __device__ void fill_B_lower(double* W, const int32_t* __restrict__ A, int P, in
 // =====================================================================================================
 __global__ void __launch_bounds__(la::THREADS, 1)
 chain_init_kernel(WsLayout lay, void* ws, bark_nodes_soa forest, const double* __restrict__ noise,
-                  const double* __restrict__ scale) {
+                  const double* __restrict__ scale, int skip_null) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     la::Smem& s = *reinterpret_cast<la::Smem*>(smem_raw);
     WalkNode* wn = reinterpret_cast<WalkNode*>(smem_raw + sizeof(la::Smem));  // [L]
@@ -101,6 +101,8 @@ chain_init_kernel(WsLayout lay, void* ws, bark_nodes_soa forest, const double* _
     for (int t = tid; t < m; t += la::THREADS) {
         int c = 0;
         for (int sl = 0; sl < L; ++sl) c += (forest.active[nb + (int64_t)t * L + sl] && forest.is_leaf[nb + (int64_t)t * L + sl]);
+        // skip_null (forest.py:101-111, the acquisition model's kernel): a root-only tree gets no column at all
+        if (skip_null && forest.is_leaf[nb + (int64_t)t * L]) c = 0;
         tcount[t + 1] = c;
     }
     for (int e = tid; e < lay.d; e += la::THREADS) ftc[e] = sv.ft[e];
@@ -118,13 +120,17 @@ chain_init_kernel(WsLayout lay, void* ws, bark_nodes_soa forest, const double* _
         }
         return;
     }
+    int n_null_part = 0;
     for (int t = tid; t < m; t += la::THREADS) {
         int c = tcount[t];
+        const bool null_tree = skip_null && forest.is_leaf[nb + (int64_t)t * L];
+        n_null_part += null_tree;
         for (int sl = 0; sl < L; ++sl) {
             const int64_t g = nb + (int64_t)t * L + sl;
-            cv.colmap[t * L + sl] = (forest.active[g] && forest.is_leaf[g]) ? (uint16_t)(c++) : NO_COL;
+            cv.colmap[t * L + sl] = (!null_tree && forest.active[g] && forest.is_leaf[g]) ? (uint16_t)(c++) : NO_COL;
         }
     }
+    const int m_eff = max(1, m - (int)block_sum((double)n_null_part, s.red));  // trees that count (m unless skip_null)
     for (int w = tid; w < P / 32; w += la::THREADS) {
         const int lo = w * 32;
         cv.colused[w] = (ptot >= lo + 32) ? 0xFFFFFFFFu : (ptot <= lo ? 0u : ((1u << (ptot - lo)) - 1u));
@@ -185,7 +191,7 @@ chain_init_kernel(WsLayout lay, void* ws, bark_nodes_soa forest, const double* _
 
     // ---- 4. Binv = (c I + A)^-1, ldt, q, mll
     const double sig = noise[chain] + 1e-6;
-    const double c = sig * (double)m / scale[chain];
+    const double c = sig * (double)m_eff / scale[chain];
     for (int64_t e = tid; e < (int64_t)P * P; e += la::THREADS) {
         const int r = (int)(e / P), k = (int)(e % P);
         cv.Binv[e] = (r == k) ? 1.0 / c : 0.0;
@@ -520,6 +526,12 @@ size_t bark_mcmc_workspace_bytes(const bark_mcmc_dims* dims) {
 int bark_mcmc_init(const bark_mcmc_dims* dims, void* workspace, bark_nodes_soa forest, const double* X,
                    const double* y, const double* bounds, const int32_t* feat_types, const double* noise,
                    const double* scale, void* stream) {
+    return bark_mcmc_init_ex(dims, workspace, forest, X, y, bounds, feat_types, noise, scale, 0, stream);
+}
+
+int bark_mcmc_init_ex(const bark_mcmc_dims* dims, void* workspace, bark_nodes_soa forest, const double* X,
+                      const double* y, const double* bounds, const int32_t* feat_types, const double* noise,
+                      const double* scale, int32_t flags, void* stream) {
     BARK_CHECK_ARG(check_dims(dims), "bad dims (chains 1..65535, node_limit 3..255, p_cap multiple of 64 in 64..8192)");
     BARK_CHECK_ARG(workspace && X && y && feat_types && noise && scale && forest.is_leaf, "null pointer");
     const WsLayout lay = make_layout(*dims);
@@ -529,7 +541,8 @@ int bark_mcmc_init(const bark_mcmc_dims* dims, void* workspace, bark_nodes_soa f
     const size_t smem = sizeof(la::Smem) + (size_t)lay.L * sizeof(WalkNode) + (size_t)(lay.d + lay.m + 2) * sizeof(int);
     BARK_CHECK_ARG(smem <= 227 * 1024, "d + m too large for the init kernel's shared memory");
     BARK_CUDA(cudaFuncSetAttribute(chain_init_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    chain_init_kernel<<<(unsigned)dims->chains, la::THREADS, smem, st>>>(lay, workspace, forest, noise, scale);
+    chain_init_kernel<<<(unsigned)dims->chains, la::THREADS, smem, st>>>(lay, workspace, forest, noise, scale,
+                                                                         (flags & BARK_INIT_SKIP_NULL) ? 1 : 0);
     BARK_LAUNCH_CHECK();
     return BARK_OK;
 }

@@ -67,7 +67,8 @@ def raise_for_status(status: np.ndarray):
 class ChainState:
     """Device-resident state of `chains` MCMC chains (forest SoA + leaf-space workspace)."""
 
-    def __init__(self, forest: np.ndarray, noise, scale, X, y, bounds, feat_types, p_cap=None, device=None):
+    def __init__(self, forest: np.ndarray, noise, scale, X, y, bounds, feat_types, p_cap=None, device=None,
+                 skip_null=False):
         torch = _lib.require_cuda()
         self.lib = _lib.load()
         self.device = torch.device(device or "cuda")
@@ -92,9 +93,10 @@ class ChainState:
         scale_d = _as_device_f64(np.reshape(scale, -1), self.device)
         if noise_d.numel() != self.chains or scale_d.numel() != self.chains:
             raise ValueError("noise and scale must have one entry per chain")
-        _lib.check(self.lib.bark_mcmc_init(C.byref(self.dims), _ptr(self.ws), self.dforest.soa(), _ptr(self.X),
-                                           _ptr(self.y), _ptr(self.bounds), _ptr(self.ft), _ptr(noise_d), _ptr(scale_d),
-                                           _stream()))
+        # skip_null: root-only trees carry no column (the acquisition model's kernel); export-only state
+        _lib.check(self.lib.bark_mcmc_init_ex(C.byref(self.dims), _ptr(self.ws), self.dforest.soa(), _ptr(self.X),
+                                              _ptr(self.y), _ptr(self.bounds), _ptr(self.ft), _ptr(noise_d), _ptr(scale_d),
+                                              _lib.INIT_SKIP_NULL if skip_null else 0, _stream()))
 
     def sweeps(self, params: BARKTrainParams, n_sweeps: int, seed: int, chain_offset=0, sweep_offset=0, tape=None,
                trace=None):

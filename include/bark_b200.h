@@ -132,6 +132,14 @@ int bark_mcmc_init(const bark_mcmc_dims* dims, void* workspace, bark_nodes_soa f
                    const double* y, const double* bounds, const int32_t* feat_types, const double* noise,
                    const double* scale, void* stream);
 
+/* Same with flags.  BARK_INIT_SKIP_NULL: root-only trees get no leaf column and do not count in m, i.e. the state
+ * is the one of the kernel of batched_forest_gram_matrix_no_null (src/bark/forest.py:101-111) that the acquisition
+ * model uses (src/bark/optimizer/opt_model.py:54-59).  Such a state is for bark_kinv_export only (no sweeps). */
+#define BARK_INIT_SKIP_NULL 1
+int bark_mcmc_init_ex(const bark_mcmc_dims* dims, void* workspace, bark_nodes_soa forest, const double* X,
+                      const double* y, const double* bounds, const int32_t* feat_types, const double* noise,
+                      const double* scale, int32_t flags, void* stream);
+
 /* Run `n_sweeps` sweeps (m tree MH steps + 1 noise/scale MH step each, bark_sampler.py:216-284) on every
  * chain, device-resident.  RNG: Philox4x32-10 keyed by (seed, chain_offset + chain) and counted by
  * (sweep_offset + sweep, tree, slot) unless `tape` != NULL, in which case every random number is read from
@@ -161,6 +169,17 @@ int bark_mcmc_read(const bark_mcmc_dims* dims, const void* workspace, double* no
  * Binv (p_cap,p_cap) f64, colmap (m,node_limit) i32 (-1 = none), bits (p_cap, ceil(n/32)) u32. */
 int bark_mcmc_export(const bark_mcmc_dims* dims, const void* workspace, int64_t chain, int32_t* A, double* Binv,
                      int32_t* colmap, uint32_t* bits, void* stream);
+
+/* ---- inputs of the acquisition model (src/bark/optimizer/opt_model.py:54-59,83,101)
+ * For every posterior sample of a workspace initialised by bark_mcmc_init[_ex] over the sample forests:
+ *   kinv   (samples, n, n) f64 = K^-1,  K = scale * K0 + (1e-6 + noise) I   (np.linalg.inv at opt_model.py:59),
+ *   kinv_y (samples, n)    f64 = K^-1 y   (the reference's lin_term is scale * K^-1 y, :101; quadr_term -scale^2 K^-1, :83)
+ * from the leaf-space state by Woodbury: K^-1 = (I - Z B^-1 Z^T) / (noise + 1e-6) -- B is P x P with cond(B) << cond(K).
+ * leaves (samples, n, m) u32: bark_traverse of the sample forests on the training inputs.  Either output may be NULL.
+ * scratch: bark_kinv_scratch_bytes(dims) bytes. */
+size_t bark_kinv_scratch_bytes(const bark_mcmc_dims* dims);
+int bark_kinv_export(const bark_mcmc_dims* dims, const void* workspace, const uint32_t* leaves, double* kinv,
+                     double* kinv_y, void* scratch, void* stream);
 
 /* ---- a14-a15: posterior predictive (forest_predict, src/bark/tree_kernels/tree_gps.py:80-113;
  *               mixture_of_gaussians_as_normal :116-131; _predict src/bofire_mixed/surrogates/bark.py:71-94) */

@@ -521,3 +521,29 @@ def test_prior_surrogate_and_checkpoint_resume(tmp_path):
     assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
     sur2.fit(X, y_raw)
     assert sur2.bark_params.warmup_steps == 0 and sur2.forest.shape == (2, 2, 12, 100)
+
+
+# ------------------------------------------------------------ acquisition-model inputs
+@pytest.mark.parametrize("n,dims,m", [(60, (3, 1), 12), (257, (4, 0), 40)])
+def test_acquisition_inputs_match_oracle(n, dims, m):
+    """K^-1, -s^2 K^-1 and s K^-1 y of the no-null kernel per posterior sample (opt_model.py:54-59,83,101) from the
+    leaf-space state (Woodbury) against the oracle's dense np.linalg.inv."""
+    X, y, bounds, ft, _ = O.synthetic_problem(n, dim=dims[0], cat_dim=dims[1], num_cat=4, m_true=10, seed=6)
+    chains = 3
+    f0 = np.tile(O.create_empty_forest(m), (chains, 1, 1))
+    # few sweeps from the empty forest: some trees are still root-only, which is what "no_null" is about
+    p = B.BARKTrainParams(warmup_steps=3, num_samples=2, steps_per_sample=2, num_chains=chains)
+    ns, noise, scale = B.run_bark_sampler((f0, np.full(chains, 0.1), np.full(chains, 1.0)), (X, y), (bounds, ft), p, seed=8)
+    n_null = ns[..., 0]["is_leaf"].sum(axis=-1)
+    assert n_null.max() > 0 and n_null.min() < m
+    y_raw = (y * 3.0 + 2.0).reshape(-1, 1)
+    got = B.gp_sample_inverses((ns, noise, scale), (X, y_raw), (bounds, ft))
+    want = O.acquisition_inputs((ns, noise, scale), (X, y_raw), ft)
+    for k in ("K_inv", "quadr_term", "lin_term", "const_term"):
+        assert got[k].shape == want[k].shape, k
+        err = np.abs(got[k] - want[k]).max() / np.abs(want[k]).max()
+        assert err < 1e-9, (k, err)
+    # an inverse is an inverse: K_inv @ K = I with K rebuilt on the GPU
+    K0 = B.batched_forest_gram_matrix_no_null(ns.reshape(-1, m, 100), X, X, ft)
+    K = scale.reshape(-1)[:, None, None] * K0 + (1e-6 + noise.reshape(-1))[:, None, None] * np.eye(n)
+    assert np.abs(got["K_inv"] @ K - np.eye(n)).max() < 1e-8
