@@ -26,8 +26,9 @@ constexpr int PU_N = 256;           // Binv columns per accumulator tile (UMMA N
 constexpr int PU_KB = 128;          // K bytes per operand tile (one SWIZZLE_128B atom row)
 constexpr int PU_SLICES = 7;        // base-256 digit planes
 constexpr int PU_MAX_STAGES = 4;    // ring stages; one stage = one K tile of one (column tile, digit plane)
-constexpr int PU_WALK_GROUPS = 4;   // threads per candidate: walk (trees t = g mod 4) and epilogue (column chunks j = g mod 4)
-constexpr int PU_THREADS = 576;     // warps 0-3 and 6-17: walk + epilogue groups, 4: MMA issue, 5: TMA producer
+constexpr int PU_WALK_GROUPS = 4;   // threads per candidate: walk (trees t = g mod 4) and epilogue (column chunks j = g mod 4);
+                                    // 6 groups measured the same (the walk is issue / LSU bound, not latency bound)
+constexpr int PU_THREADS = 64 + 128 * PU_WALK_GROUPS;  // warps 0-3 and 6..: walk + epilogue groups, 4: MMA issue, 5: TMA producer
 constexpr int PU_A_TILE = PU_ROWS * PU_KB;  // 16 KB
 constexpr int PU_B_TILE = PU_N * PU_KB;     // 32 KB
 constexpr int PU_RING_MAX = 128 * 1024;
@@ -363,7 +364,7 @@ predict_umma_kernel(WsLayout lay, const void* ws, const WalkNode* __restrict__ t
                 int a = acc[s];
 #pragma unroll
                 for (int j = 0; j < PU_N / 32; ++j) {
-                    if ((j & (PU_WALK_GROUPS - 1)) != wg) continue;  // warp-uniform
+                    if ((j % PU_WALK_GROUPS) != wg) continue;  // warp-uniform
                     const uint32_t bits = (uint32_t)(zm[j >> 1] >> (32 * (j & 1)));
                     if (__any_sync(0xffffffffu, bits != 0u)) {
                         uint32_t v[32];
