@@ -739,9 +739,14 @@ sweep_trees_kernel(WsLayout lay, void* ws, bark_nodes_soa forest, bark_params pr
                         if (r < R) *cluster.map_shared_rank(&ctl->dec, r) = dd;
                 }
             }
-            // meanwhile (or right after, with one CTA per chain) the generator rank prepares the next proposal
-            if (cr == gen_rank && t + 1 < m) generate(t + 1);
-            csync();  // (2b) decision visible on every CTA
+            // meanwhile (or right after, with one CTA per chain) the generator rank prepares the next proposal and
+            // publishes it SPECULATIVELY (its free column assumes a rejection, the common case): barrier (2b) then
+            // makes both the decision and the next proposal visible, and a rejected proposal needs no barrier (3)
+            if (cr == gen_rank && t + 1 < m) {
+                generate(t + 1);
+                publish(t + 1);
+            }
+            csync();  // (2b) decision (and the speculative next proposal) visible on every CTA
             const Decision dec = ctl->dec;
             accept = dec.accept != 0;
             new_q = dec.new_q; new_ldt = dec.new_ldt; new_mll = dec.new_mll;
@@ -755,8 +760,10 @@ sweep_trees_kernel(WsLayout lay, void* ws, bark_nodes_soa forest, bark_params pr
                     colused_s[b >> 5] &= ~(1u << (b & 31));
                 }
             }
-            __syncthreads();
-            if (cr == gen_rank && t + 1 < m) publish(t + 1);
+            if (accept) {  // the allocator changed: the next proposal gets its column again
+                __syncthreads();
+                if (cr == gen_rank && t + 1 < m) publish(t + 1);
+            }
         }
 
         if (tid == 0) {
@@ -1021,7 +1028,10 @@ sweep_trees_kernel(WsLayout lay, void* ws, bark_nodes_soa forest, bark_params pr
             }
         }
         PHASE_MARK(8);
-        csync();  // (3) peer's global-memory edits and the next proposal visible; exchanged vectors free for reuse
+        // (3) after an accepted proposal: peer's global-memory edits and the re-published next proposal visible,
+        // exchanged vectors free for reuse.  A rejected one wrote nothing that the next iteration reads before its
+        // own barrier (1), and nobody reads the exchanged vectors after (2b).
+        if (accept) csync();
     }
     PHASE_MARK(9);
     __syncthreads();
