@@ -547,3 +547,20 @@ def test_acquisition_inputs_match_oracle(n, dims, m):
     K0 = B.batched_forest_gram_matrix_no_null(ns.reshape(-1, m, 100), X, X, ft)
     K = scale.reshape(-1)[:, None, None] * K0 + (1e-6 + noise.reshape(-1))[:, None, None] * np.eye(n)
     assert np.abs(got["K_inv"] @ K - np.eye(n)).max() < 1e-8
+
+
+def test_cluster_size_does_not_change_the_chain(monkeypatch):
+    """1, 2 or 4 CTAs per chain (BARK_SWEEP_CLUSTER) only change how the leaf-space linear algebra is shared out: the
+    sampled forests are byte-identical and the hyper-parameter samples agree to rounding."""
+    X, y, bounds, ft, _ = O.synthetic_problem(300, dim=5, cat_dim=1, num_cat=4, m_true=20, seed=12)
+    chains, m = 3, 40
+    p = B.BARKTrainParams(warmup_steps=25, num_samples=2, steps_per_sample=5, num_chains=chains)
+    f0 = np.tile(O.create_empty_forest(m), (chains, 1, 1))
+    runs = {}
+    for r in ("1", "2", "4"):
+        monkeypatch.setenv("BARK_SWEEP_CLUSTER", r)
+        runs[r] = B.run_bark_sampler((f0, np.full(chains, 0.1), np.full(chains, 1.0)), (X, y), (bounds, ft), p, seed=77)
+    monkeypatch.delenv("BARK_SWEEP_CLUSTER")
+    for r in ("2", "4"):
+        assert runs[r][0].tobytes() == runs["1"][0].tobytes(), f"forests differ between 1 and {r} CTAs per chain"
+        assert np.allclose(runs[r][1], runs["1"][1], rtol=1e-9, atol=0)
