@@ -71,9 +71,9 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     return ok != 0;
 }
 // Warp-uniform wait: every lane of the calling warp waits on the SAME barrier (no divergence inside).
-// Bounded: a wait that does not complete within ~2^26 probes flags BARK_ST_TIMEOUT and gives up instead of
+// Bounded: a wait that does not complete within ~2^22 probes flags BARK_ST_TIMEOUT and gives up instead of
 // hanging the GPU (results of that chain are then invalid and the host raises).
-constexpr unsigned SW_WAIT_LIMIT = 1u << 26;
+constexpr unsigned SW_WAIT_LIMIT = 1u << 22;
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, unsigned* status) {
     unsigned spins = 0;
     while (!mbar_try_wait(bar, parity)) {
@@ -896,57 +896,35 @@ sweep_trees_kernel(WsLayout lay, void* ws, bark_nodes_soa forest, bark_params pr
                         }
                     } else if (wid < SW_NCW) {
                         const int ifirst = use_ring ? (int)((wid + SW_NCW - (ring_base % SW_NCW)) % SW_NCW) : wid;
-                        int prev_slot = -1;
                         for (int i = ifirst; i < nrows; i += SW_NCW) {
                             const int q = qfirst + i * R;
                             const double ad = al * Wd[q] + be * Wv[q], av = be * Wd[q] + ga * Wv[q];
                             const int len2 = ((min(q + 1, c1) - c0) + 1) & ~1;
+                            double* grow = cv.Binv + (size_t)q * P + c0;
+                            const double* row = grow;
+                            int slot = 0;
                             if (use_ring) {
                                 const uint32_t use = ring_base + (uint32_t)i;
-                                const int slot = (int)(use % (uint32_t)nslot);
+                                slot = (int)(use % (uint32_t)nslot);
                                 mbar_wait(full_bar + slot, (use / (uint32_t)nslot) & 1u, &sc->status);
-                                double* row = reinterpret_cast<double*>(ring + (size_t)slot * slot_bytes);
-                                for (int kk = lane * 2; kk < len2; kk += 64) {
-                                    double2 x = *reinterpret_cast<double2*>(row + kk);
-                                    const double2 dd = *reinterpret_cast<const double2*>(Wd + c0 + kk);
-                                    const double2 vv = *reinterpret_cast<const double2*>(Wv + c0 + kk);
-                                    x.x -= ad * dd.x + av * vv.x;
-                                    x.y -= ad * dd.y + av * vv.y;
-                                    *reinterpret_cast<double2*>(row + kk) = x;
-                                }
-                                fence_proxy_async();  // generic-proxy writes to the slot -> bulk store (async proxy) reads
+                                row = reinterpret_cast<const double*>(ring + (size_t)slot * slot_bytes);
+                            }
+                            // updated rows go straight from registers to global memory: the slot is free as soon as it
+                            // has been read (a deferred release would dead-lock when a warp owns a single slot)
+                            for (int kk = lane * 2; kk < len2; kk += 64) {
+                                double2 x = use_ring ? *reinterpret_cast<const double2*>(row + kk) : ldcg2(row + kk);
+                                const double2 dd = *reinterpret_cast<const double2*>(Wd + c0 + kk);
+                                const double2 vv = *reinterpret_cast<const double2*>(Wv + c0 + kk);
+                                x.x -= ad * dd.x + av * vv.x;
+                                x.y -= ad * dd.y + av * vv.y;
+                                __stcg(reinterpret_cast<double2*>(grow + kk), x);
+                            }
+                            if (use_ring) {
                                 __syncwarp();
-                                if (lane == 0) {
-                                    bulk_s2g(cv.Binv + (size_t)q * P + c0, row, (uint32_t)len2 * 8u);
-                                    bulk_commit();
-                                    // release the PREVIOUS slot of this warp once its store has read shared memory
-                                    // (at most one store group stays pending, so this one overlaps the next row)
-                                    if (prev_slot >= 0) {
-                                        bulk_wait_read1();
-                                        mbar_arrive(empty_bar + prev_slot);
-                                    }
-                                }
-                                prev_slot = slot;
-                            } else {
-                                double* row = cv.Binv + (size_t)q * P + c0;
-                                for (int kk = lane * 2; kk < len2; kk += 64) {
-                                    double2 x = ldcg2(row + kk);
-                                    const double2 dd = *reinterpret_cast<const double2*>(Wd + c0 + kk);
-                                    const double2 vv = *reinterpret_cast<const double2*>(Wv + c0 + kk);
-                                    x.x -= ad * dd.x + av * vv.x;
-                                    x.y -= ad * dd.y + av * vv.y;
-                                    __stcg(reinterpret_cast<double2*>(row + kk), x);
-                                }
+                                if (lane == 0) mbar_arrive(empty_bar + slot);
                             }
                         }
-                        if (use_ring && lane == 0) {
-                            if (prev_slot >= 0) {
-                                bulk_wait_read0();
-                                mbar_arrive(empty_bar + prev_slot);
-                            }
-                            bulk_wait0();  // this warp's row stores are complete
-                            fence_proxy_async();
-                        }
+                        fence_proxy_async();  // generic stores of the rows -> later bulk loads (async proxy)
                     }
                     if (use_ring) ring_base += (uint32_t)nrows;
                 }

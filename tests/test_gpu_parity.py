@@ -564,3 +564,17 @@ def test_cluster_size_does_not_change_the_chain(monkeypatch):
     for r in ("2", "4"):
         assert runs[r][0].tobytes() == runs["1"][0].tobytes(), f"forests differ between 1 and {r} CTAs per chain"
         assert np.allclose(runs[r][1], runs["1"][1], rtol=1e-9, atol=0)
+
+
+def test_sampler_wide_forest_unpaired_panels():
+    """More than 512 leaf columns in use (m = 320 trees): the matvec / update passes run panel by panel instead of
+    with paired row prefixes; still the oracle's trajectory byte for byte."""
+    want, trace_o, got, _ = replay_case(n=200, dim=4, cat=0, m=320, chains=2, warm=9, ns=1, sps=3, seed=21)
+    ns_g, noise_g, scale_g, trace_g, info = got
+    leaves = (ns_g["active"] & ns_g["is_leaf"]).sum(axis=(-1, -2))
+    assert leaves.max() > 512, leaves  # the point of the test
+    fin = np.isfinite(trace_o[..., 0])
+    rel = np.abs(trace_g[..., 1][fin] - trace_o[..., 1][fin]) / np.maximum(np.abs(trace_o[..., 1][fin]), 1e-300)
+    assert rel.max() < 1e-9, rel.max()
+    assert not (trace_o[..., 2] != trace_g[..., 2]).any()
+    assert ns_g.tobytes() == want[0].tobytes()
