@@ -578,3 +578,26 @@ def test_sampler_wide_forest_unpaired_panels():
     assert rel.max() < 1e-9, rel.max()
     assert not (trace_o[..., 2] != trace_g[..., 2]).any()
     assert ns_g.tobytes() == want[0].tobytes()
+
+
+@pytest.mark.parametrize("m", [60, 130, 210, 320])
+def test_predict_tensor_core_tilings(m):
+    """Leaf-column extents that give 2, 3, 4 and 6 K tiles (one, two or three 256-column tiles, the last one half
+    full or full) in the tcgen05 predict kernel: equal to the FP64 gather kernel and to the oracle."""
+    import torch
+    X, y, bounds, ft, _ = O.synthetic_problem(150, dim=4, cat_dim=1, num_cat=4, m_true=10, seed=m)
+    chains = 2
+    f0 = np.tile(O.create_empty_forest(m), (chains, 1, 1))
+    p = B.BARKTrainParams(warmup_steps=10, num_samples=1, steps_per_sample=2, num_chains=chains)
+    ns, noise, scale = B.run_bark_sampler((f0, np.full(chains, 0.1), np.full(chains, 1.0)), (X, y), (bounds, ft), p, seed=m)
+    ps = B.PosteriorState((ns, noise, scale), (X, y), ft, 5)
+    assert ps.prep is not None
+    ps_ref = B.PosteriorState((ns, noise, scale), (X, y), ft, 5, tensor_cores=False)
+    rng = np.random.default_rng(m)
+    cand = np.hstack([rng.random((301, 4)), rng.integers(0, 4, size=(301, 1)).astype(np.float64)])
+    cd = torch.tensor(cand, device="cuda")
+    mu, var = (t.cpu().numpy() for t in ps.predict_device(cd, mode=0))
+    mu2, var2 = (t.cpu().numpy() for t in ps_ref.predict_device(cd, mode=0))
+    assert np.allclose(mu, mu2, rtol=1e-12, atol=1e-12) and np.allclose(var, var2, rtol=1e-9, atol=1e-12)
+    omu, ovar = O.forest_predict((ns, noise, scale), (X, y.reshape(-1, 1)), cand[:40], ft)
+    assert np.allclose(mu[:, :40], omu, rtol=1e-9, atol=1e-9) and np.allclose(var[:, :40], ovar, rtol=1e-7, atol=1e-9)
