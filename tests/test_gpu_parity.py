@@ -408,12 +408,13 @@ def test_sampler_ragged_sizes():
 
 
 # ------------------------------------------------------------ full-size properties (BASELINE config 4 shape)
-def test_full_size_state_properties():
-    """N=2000, m=200 (BASELINE config 4's shape, 4 of the 64 chains): after free-running sweeps the leaf-space state
+@pytest.mark.parametrize("n,dims,m,chains", [(2000, (10, 0), 200, 4), (500, (6, 4), 100, 8)])
+def test_full_size_state_properties(n, dims, m, chains):
+    """BASELINE config 4's shape (N=2000, m=200, continuous; 4 of the 64 chains) and config 3's (N=500, 6 continuous
+    + 4 categorical features with 5 levels, m=100; 8 of the 32 chains): after free-running sweeps the leaf-space state
     is exactly the one of the final forest (integer parts bit-exact), B^-1 is an inverse, and the running log-MLL
     equals both the GPU from-scratch evaluation and the oracle's dense Cholesky value to 1e-9."""
-    n, m, chains = 2000, 200, 4
-    X, y, bounds, ft, _ = O.synthetic_problem(n, dim=10, cat_dim=0, m_true=50, seed=0)
+    X, y, bounds, ft, _ = O.synthetic_problem(n, dim=dims[0], cat_dim=dims[1], num_cat=5, m_true=50, seed=0)
     f0 = np.tile(O.create_empty_forest(m), (chains, 1, 1))
     st = S.ChainState(f0, np.full(chains, 0.1), np.full(chains, 1.0), X, y, bounds, ft)
     p = B.BARKTrainParams(num_chains=chains)
