@@ -37,7 +37,7 @@ struct __align__(16) Smem {
     double red[32];
 };
 
-enum { ACC_SUB = 0, ACC_SET = 1 };
+enum { ACC_SUB = 0, ACC_SET = 1, ACC_ADD = 2 };
 
 // C[0:mr, 0:nc] (-)= A[0:mr, 0:K] * B[0:nc, 0:K]^T.  Row-major, leading dimensions lda/ldb/ldc.
 // lower_only: write only entries with column <= row (diagonal tiles of a symmetric update).
@@ -126,7 +126,7 @@ __device__ __forceinline__ void gemm_nt_tile(double* C, int64_t ldc, const doubl
 #pragma unroll
     for (int xh = 0; xh < 4; xh += 2) {
         double old[2][4][2];
-        if (MODE == ACC_SUB) {
+        if (MODE != ACC_SET) {
 #pragma unroll
             for (int xx = 0; xx < 2; ++xx)
 #pragma unroll
@@ -160,8 +160,8 @@ __device__ __forceinline__ void gemm_nt_tile(double* C, int64_t ldc, const doubl
                 double* p = C + (int64_t)r * ldc + c;
                 const bool ok0 = c < nc && (!lower_only || c <= r);
                 const bool ok1 = c + 1 < nc && (!lower_only || c + 1 <= r);
-                const double v0 = (MODE == ACC_SUB) ? old[xx][y][0] - acc[x][y][0] : acc[x][y][0];
-                const double v1 = (MODE == ACC_SUB) ? old[xx][y][1] - acc[x][y][1] : acc[x][y][1];
+                const double v0 = (MODE == ACC_SUB) ? old[xx][y][0] - acc[x][y][0] : (MODE == ACC_ADD) ? old[xx][y][0] + acc[x][y][0] : acc[x][y][0];
+                const double v1 = (MODE == ACC_SUB) ? old[xx][y][1] - acc[x][y][1] : (MODE == ACC_ADD) ? old[xx][y][1] + acc[x][y][1] : acc[x][y][1];
                 if (ok0 && ok1 && vec_ok) {
                     __stcg(reinterpret_cast<double2*>(p), make_double2(v0, v1));
                 } else {
@@ -474,6 +474,53 @@ __device__ double block_sweep(double* W, int64_t ld, int n, double* CK, double* 
     if (quad) *quad = q;
     return logdet;
 }
+
+
+// One Newton-Schulz step on an approximate inverse X of the SPD matrix B = c I + A (A integer, lower triangle valid):
+//     X <- X + (I - X B) X
+// squares the residual |I - X B| (the block Gauss-Jordan inverse leaves ~cond(B)^2 eps, which is no longer small
+// against the 1e-9 parity bar once cond(B) reaches ~1e4, i.e. for very small noise).  X: n x n, both triangles
+// valid on entry and on exit; Bf, R: n x n scratch (leading dimension ld each).  Tiles are shared by the team.
+template <class Team>
+__device__ void refine_inverse(double* X, double* Bf, double* R, const int32_t* A, double c, int64_t ld, int n, Smem& s,
+                               const Team& team) {
+    const int tid = threadIdx.x;
+    const int trank = team.rank(), tsize = team.size();
+    // Bf = c I + A (both triangles), R = I
+    for (int r = trank; r < n; r += tsize)
+        for (int k = tid; k < n; k += THREADS) {
+            const int32_t a = (k <= r) ? __ldcg(A + (int64_t)r * ld + k) : __ldcg(A + (int64_t)k * ld + r);
+            __stcg(Bf + (int64_t)r * ld + k, (double)a + (r == k ? c : 0.0));
+            __stcg(R + (int64_t)r * ld + k, r == k ? 1.0 : 0.0);
+        }
+    team.sync();
+    const int nt = (n + TILE - 1) / TILE;
+    // R -= X Bf^T  (Bf symmetric)  ->  R = I - X B
+    for (int idx = trank; idx < nt * nt; idx += tsize) {
+        const int ti = (idx / nt) * TILE, tj = (idx % nt) * TILE;
+        gemm_nt_tile<ACC_SUB>(R + (int64_t)ti * ld + tj, ld, X + (int64_t)ti * ld, ld, Bf + (int64_t)tj * ld, ld,
+                              min(TILE, n - ti), min(TILE, n - tj), n, false, s);
+    }
+    team.sync();
+    // Bf <- X (Bf is dead), then Bf += R X^T (X symmetric)  ->  Bf = X + (I - X B) X
+    for (int r = trank; r < n; r += tsize)
+        for (int k = tid; k < n; k += THREADS) __stcg(Bf + (int64_t)r * ld + k, __ldcg(X + (int64_t)r * ld + k));
+    team.sync();
+    for (int idx = trank; idx < nt * nt; idx += tsize) {
+        const int ti = (idx / nt) * TILE, tj = (idx % nt) * TILE;
+        gemm_nt_tile<ACC_ADD>(Bf + (int64_t)ti * ld + tj, ld, R + (int64_t)ti * ld, ld, X + (int64_t)tj * ld, ld,
+                              min(TILE, n - ti), min(TILE, n - tj), n, false, s);
+    }
+    team.sync();
+    // X <- symmetrised refined inverse
+    for (int r = trank; r < n; r += tsize)
+        for (int k = tid; k < n; k += THREADS)
+            __stcg(X + (int64_t)r * ld + k, 0.5 * (__ldcg(Bf + (int64_t)r * ld + k) + __ldcg(Bf + (int64_t)k * ld + r)));
+    team.sync();
+}
+
+// cond(B) <= (c + n_points) / c for B = c I + Z^T Z: above this bound the Gauss-Jordan inverse is refined
+constexpr double REFINE_COND = 3000.0;
 
 }  // namespace la
 }  // namespace bark

@@ -203,6 +203,7 @@ chain_init_kernel(WsLayout lay, void* ws, bark_nodes_soa forest, const double* _
     if (tid == 0) *stp = 0;
     __syncthreads();
     const double logdet = la::block_sweep<true>(cv.Binv, P, ptot, cv.CK, cv.GK, cv.DG, nullptr, nullptr, s, stp, la::SoloTeam());
+    if (((double)n + c) / c > la::REFINE_COND) la::refine_inverse(cv.Binv, cv.Wk, cv.S2, cv.A, c, P, ptot, s, la::SoloTeam());
     const double q = matvec_w_q(cv.Binv, P, ptot, cv.b, cv.w, s.red);
     const double ldt = logdet - (double)ptot * log(c);
     if (tid == 0) {
@@ -346,6 +347,7 @@ hyper_refresh_kernel(WsLayout lay, void* ws) {
             __stcg(cv.Binv + (size_t)r * P + k, (double)__ldcg(cv.A + (size_t)r * P + k) + (r == k ? c2 : 0.0));
     team.sync();
     const double logdet_f = la::block_sweep<true>(cv.Binv, P, ph, cv.CK, cv.GK, cv.DG, nullptr, nullptr, s, &sc->status, team);
+    if (((double)n + c2) / c2 > la::REFINE_COND) la::refine_inverse(cv.Binv, cv.Wk, cv.S2, cv.A, c2, P, ph, s, team);
     for (int k = ph + trank * la::THREADS + tid; k < P; k += tsize * la::THREADS) __stcg(cv.Binv + (size_t)k * P + k, 1.0 / c2);
     // w = Binv b, rows split over the cluster
     for (int r = trank * nw + wid; r < ph; r += tsize * nw) {

@@ -32,7 +32,7 @@ struct WsLayout {
     int64_t chains, n, d, m, L, P, wd, npad;
     size_t off_xt, off_y, off_bounds, off_ft;  // shared
     size_t off_chain0, chain_stride;           // per chain block
-    size_t off_binv, off_wk, off_a, off_bits, off_ck, off_gk, off_dg, off_b, off_w, off_yv, off_colmap, off_colused, off_sc;
+    size_t off_binv, off_wk, off_s2, off_a, off_bits, off_ck, off_gk, off_dg, off_b, off_w, off_yv, off_colmap, off_colused, off_sc;
     size_t total;
 };
 
@@ -65,12 +65,15 @@ __host__ __device__ inline WsLayout make_layout(const bark_mcmc_dims& dm) {
     w.off_colused = c; c = align256(c + (P / 32) * sizeof(uint32_t));
     w.off_sc = c;      c = align256(c + sizeof(ChainScalars));
     w.chain_stride = c;
-    w.total = w.off_chain0 + (size_t)w.chains * w.chain_stride;
+    // second scratch matrix per chain (inverse refinement): kept OUTSIDE the per-chain blocks so that the layout of the
+    // hot state (and with it the L2 behaviour of the sweep kernel) does not depend on it
+    w.off_s2 = w.off_chain0 + (size_t)w.chains * w.chain_stride;
+    w.total = w.off_s2 + (size_t)w.chains * align256(P * P * sizeof(double));
     return w;
 }
 
 struct ChainView {
-    double* Binv; double* Wk; int32_t* A; uint32_t* bits; double* CK; double* GK; double* DG;
+    double* Binv; double* Wk; double* S2; int32_t* A; uint32_t* bits; double* CK; double* GK; double* DG;
     double* b; double* w; double* yv; uint16_t* colmap; uint32_t* colused; ChainScalars* sc;
 };
 
@@ -79,6 +82,7 @@ __host__ __device__ inline ChainView chain_view(const WsLayout& w, void* ws, int
     ChainView v;
     v.Binv = (double*)(base + w.off_binv);
     v.Wk = (double*)(base + w.off_wk);
+    v.S2 = (double*)((unsigned char*)ws + w.off_s2 + (size_t)chain * align256((size_t)w.P * w.P * sizeof(double)));
     v.A = (int32_t*)(base + w.off_a);
     v.bits = (uint32_t*)(base + w.off_bits);
     v.CK = (double*)(base + w.off_ck);
