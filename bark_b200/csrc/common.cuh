@@ -55,6 +55,17 @@ __device__ __forceinline__ double warp_sum(double v) {
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
 }
+// two independent sums, interleaved step by step (the shuffle chains overlap instead of running back to back);
+// each result is bit-identical to warp_sum of the same value
+__device__ __forceinline__ void warp_sum2(double& a, double& b) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double ta = __shfl_xor_sync(0xffffffffu, a, o);
+        const double tb = __shfl_xor_sync(0xffffffffu, b, o);
+        a += ta;
+        b += tb;
+    }
+}
 __device__ __forceinline__ int warp_sum_int(int v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -156,15 +156,15 @@ __device__ __forceinline__ double2 ldcg2(const double* p) { return __ldcg(reinte
 // deterministic block-wide sum of two values at once (one barrier pair)
 __device__ __forceinline__ void block_sum2(double& a, double& b, double* scratch) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    a = warp_sum(a);
-    b = warp_sum(b);
+    warp_sum2(a, b);
     __syncthreads();
     if (lane == 0) { scratch[wid] = a; scratch[32 + wid] = b; }
     __syncthreads();
     const double ra = (lane < SW_WARPS) ? scratch[lane] : 0.0;
     const double rb = (lane < SW_WARPS) ? scratch[32 + lane] : 0.0;
-    a = warp_sum(ra);
-    b = warp_sum(rb);
+    a = ra;
+    b = rb;
+    warp_sum2(a, b);
 }
 
 __global__ void __launch_bounds__(SW_THREADS, 1)
@@ -552,8 +552,7 @@ sweep_trees_kernel(WsLayout lay, void* ws, bark_nodes_soa forest, bark_params pr
                                 }
                             }
                         }
-                        dotA = warp_sum(dotA);  // every lane's slot reads are complete here
-                        dotB = warp_sum(dotB);
+                        warp_sum2(dotA, dotB);  // every lane's slot reads are complete here
                         if (lane == 0) {
                             mbar_arrive(empty_bar + slot);
                             ydot[qA] += dotA;
