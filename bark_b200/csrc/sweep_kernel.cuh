@@ -1,20 +1,24 @@
 // Tree sweep: the m tree MH steps of one sweep of one chain (bark_sampler.py:233-264) in leaf space.
 //
-// A thread-block CLUSTER of R CTAs (R = 1 or 2; 512 threads each) owns one chain, so that 64 chains fill
-// 128 of the 148 SMs.  Only the LOWER TRIANGLE of the symmetric B^-1 is kept current (row q holds columns 0..q),
-// which halves the bytes per pass and lets 64 chains' states (~55 MB) stay L2-resident.  Rows are interleaved
-// across the cluster (row q belongs to CTA q % R):
+// A thread-block CLUSTER of R CTAs (R = 1, 2 or 4; 512 threads each) owns one chain: 64 chains fill 128 of the 148
+// SMs with R = 2, at most 37 chains use R = 4.  Only the LOWER TRIANGLE of the symmetric B^-1 is kept current (row q
+// holds columns 0..q), which halves the bytes per pass and lets 64 chains' states stay L2-resident.  Rows are
+// interleaved across the cluster (row q belongs to CTA q % R):
 //   phase 1  moved-point masks u+/u-, eta = u^T y, n_u           (redundant on every CTA; N bits)
-//   phase 2  v = Z^T u by AND+POPC over the leaf bitsets         (columns split; halves exchanged through DSMEM)
-//   phase 3  Wd = Binv d (two rows), Wv = Binv v: every streamed row prefix yields a dot product (row part)
-//            and an axpy into per-lane column accumulators (column part); partial vectors summed over the cluster
-//   phase 4  2x2 capacitance matrix, proposed log-MLL, MH accept (redundant, bitwise identical on every CTA)
+//   phase 2  v = Z^T u by AND+POPC over the leaf bitsets         (columns split; shares exchanged through DSMEM)
+//            and Wd = Binv d (two rows of the symmetric matrix)
+//   phase 3  Wv = Binv v: every streamed row prefix yields a dot product (row part) and an axpy into per-lane
+//            column accumulators (column part); partial vectors summed over the cluster through DSMEM
+//   phase 4  rank 0 alone: 2x2 capacitance matrix, proposed log-MLL, MH accept, broadcast to the cluster --
+//            while the last rank generates the NEXT tree's proposal and publishes it speculatively
 //   accept   symmetric rank-2 update of the CTA's rows of Binv; w; integer A / bitsets / forest edits
+// Cluster barriers per proposal: after phase 2, after phase 3, after phase 4, and -- only after an accepted
+// proposal -- at the end.
 //
-// The two HBM/L2-bound passes over B^-1 (matvec, rank-2 update) stream the CTA's rows through a shared-memory
-// ring with the bulk-copy engine (TMA, cp.async.bulk + mbarrier full/empty pairs): one producer warp keeps up
-// to ~170 KB of row copies in flight, 15 consumer warps reduce (or update and bulk-store back) one row each.
-// That lifts the per-SM request-tracking limit of plain loads (ncu: 29 % of DRAM peak, long-scoreboard bound).
+// The two passes over B^-1 (matvec, rank-2 update) stream the CTA's rows, paired short + long per slot, through a
+// shared-memory ring with the bulk-copy engine (TMA, cp.async.bulk + mbarrier full/empty pairs): one producer warp
+// keeps up to ~170 KB of row copies in flight, 15 consumer warps reduce one row pair each, or update it and store
+// it straight from registers.  A ring slot is always consumed by the same warp (mbarrier waits carry one parity bit).
 // State written by a peer CTA is only read after a cluster barrier (release/acquire) and through L2 (.cg).
 #pragma once
 #include <cooperative_groups.h>
@@ -89,21 +93,12 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint3
                  "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
-__device__ __forceinline__ void bulk_s2g(void* gdst, const void* smem_src, uint32_t bytes) {
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(smem_src)),
-                 "r"(bytes)
-                 : "memory");
-}
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 
-// Rank 0 of the cluster is the single decision maker: it generates the proposal and takes the MH decision, and
-// broadcasts both (with the update coefficients) to the other CTAs through DSMEM, so the CTAs of a cluster can
-// never disagree on control flow (a disagreement would dead-lock the cluster barriers).
+// Rank 0 of the cluster is the single decision maker: it takes the MH decision and broadcasts it (with the update
+// coefficients) to the other CTAs through DSMEM, as the generator rank does with the proposals, so the CTAs of a
+// cluster can never disagree on control flow (a disagreement would dead-lock the cluster barriers).
 struct Decision {
     double eta, al, be, ga, cw_d, cw_v, new_q, new_ldt, new_mll;
     int accept, pad;
@@ -821,7 +816,6 @@ sweep_trees_kernel(WsLayout lay, void* ws, bark_nodes_soa forest, bark_params pr
                     }
                 } else {
                     const int jfirst = (int)((wid + SW_NCW - (ring_base % SW_NCW)) % SW_NCW);
-                    int prev_slot = -1;
                     for (int j = jfirst; j < npairs; j += SW_NCW) {
                         const int iA = j, iB = nrows - 1 - j;
                         const int qA = qfirst + iA * R, qB = qfirst + iB * R;
