@@ -169,3 +169,19 @@ def test_prior_sampler_structure_and_depth_law():
     assert all(prior._next_power_of_2(x) == O.next_power_of_2(x) for x in range(0, 70))
     noise = bark_b200.sample_noise_prior(1.5, 5.0, 20000, np.random.default_rng(2))
     assert abs(noise.mean() - 1.5 / 5.0) < 0.01
+
+
+def test_new_entry_points_also_refuse_to_run_without_cuda():
+    """The 8f rows obey the same rule as the hot path: no GPU, no result (never a host fallback)."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("needs a machine without CUDA")
+    f = bark_b200.create_empty_forest(3)[None]
+    X, y = np.zeros((4, 2)), np.zeros((4, 1))
+    dom = (np.array([[0.0, 1.0], [0.0, 1.0]]), np.array([2, 2]))
+    with pytest.raises(_lib.BarkError):
+        bark_b200.gp_sample_inverses((f, np.ones(1), np.ones(1)), (X, y + np.arange(4)[:, None]), dom)
+    sur = bark_b200.BARKPriorSurrogate(dom, num_samples=2, num_trees=3, sample_seed=0).fit(X, y + np.arange(4)[:, None])
+    assert sur.forest.shape == (2, 3, 100)  # drawing from the prior is host code, as in the reference
+    with pytest.raises(_lib.BarkError):
+        sur.predict(X)
