@@ -602,3 +602,18 @@ def test_predict_tensor_core_tilings(m):
     assert np.allclose(mu, mu2, rtol=1e-12, atol=1e-12) and np.allclose(var, var2, rtol=1e-9, atol=1e-12)
     omu, ovar = O.forest_predict((ns, noise, scale), (X, y.reshape(-1, 1)), cand[:40], ft)
     assert np.allclose(mu[:, :40], omu, rtol=1e-9, atol=1e-9) and np.allclose(var[:, :40], ovar, rtol=1e-7, atol=1e-9)
+
+
+def test_tree_agreement_kernel_on_device():
+    """tree_model_kernel.py:16-23 with GPU tensors in and out: equal to the oracle's forest_gram_matrix bit for bit."""
+    import torch
+    X, y, bounds, ft, _ = O.synthetic_problem(150, dim=3, cat_dim=1, num_cat=4, m_true=10, seed=2)
+    forest = random_forests(1, 17, bounds, ft, sweeps=12, seed=4)[0]
+    k = B.TreeAgreementKernel(forest, ft)
+    x1 = torch.tensor(X[:97], device="cuda")
+    x2 = torch.tensor(X[40:], device="cuda", dtype=torch.float64)
+    got = k(x1, x2)
+    assert got.is_cuda and got.shape == (97, 110)
+    assert np.array_equal(got.cpu().numpy(), O.forest_gram_matrix(forest, X[:97], X[40:], ft))
+    assert np.array_equal(k.forward(x1, x1).cpu().numpy(), O.forest_gram_matrix(forest, X[:97], X[:97], ft))
+    assert torch.equal(k.forward(x1, x2, diag=True), torch.ones(97, dtype=torch.float64, device="cuda"))
