@@ -27,10 +27,10 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 # dram__bytes_read.sum + dram__bytes_write.sum of sweep_trees_kernel, one `ncu --set full` capture of this workload
-# (profiles/r1_d_ncu_full_summary.csv): the leaf-space state is L2-resident (86 % L2 hit rate), so DRAM traffic is
+# (profiles/r1_e_ncu_full_summary.csv): the leaf-space state is L2-resident (86 % L2 hit rate), so DRAM traffic is
 # far below the algorithmic bytes.
-NCU_DRAM_BYTES_PER_LAUNCH = 2.257e9
-NCU_SOURCE = "profiles/r1_d_ncu_full_summary.csv (ncu --set full, round 1)"
+NCU_DRAM_BYTES_PER_LAUNCH = 2.268e9
+NCU_SOURCE = "profiles/r1_e_ncu_full_summary.csv (ncu --set full, round 1)"
 
 METRIC = "mcmc_proposals_per_sec_full_mll"
 UNIT = "proposals/s"
