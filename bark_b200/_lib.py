@@ -49,6 +49,7 @@ SIGNATURES = {
     "bark_mll_batched": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                  c_void_p, c_void_p]),
     "bark_mcmc_workspace_bytes": (c_size_t, [C.POINTER(McmcDims)]),
+    "bark_mcmc_max_p_cap": (c_int64, [C.POINTER(McmcDims)]),
     "bark_mcmc_init": (c_int, [C.POINTER(McmcDims), c_void_p, NodesSoA, c_void_p, c_void_p, c_void_p, c_void_p,
                                c_void_p, c_void_p, c_void_p]),
     "bark_mcmc_init_ex": (c_int, [C.POINTER(McmcDims), c_void_p, NodesSoA, c_void_p, c_void_p, c_void_p, c_void_p,

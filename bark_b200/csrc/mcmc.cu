@@ -22,7 +22,7 @@
 #include "linalg.cuh"
 #include "mcmc_state.cuh"
 #include "proposal_device.cuh"
-#include "sweep_kernel.cuh"
+#include "sweep_block.cuh"
 
 namespace bark {
 
@@ -429,17 +429,59 @@ static int check_dims(const bark_mcmc_dims* dm) {
     return 1;
 }
 
-// Cluster size for the tree sweep: the largest R in {1,2,4} with chains*R CTAs resident at once (1 CTA / SM).
-static int pick_cluster_size(int64_t chains) {
+// Launch geometry of the tree sweep: proposals per block (ks: 8, or a smaller power of two when the capacity is so
+// large that eight P-vectors per matrix do not fit shared memory) and CTAs per chain (R: the largest power of two
+// <= 16 with every chain's cluster resident at once; 16 is a non-portable cluster size, opted into at launch).
+static size_t sweep_smem_budget() {
+    int dev = 0, optin = 227 * 1024;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    return (size_t)std::min(optin, 227 * 1024);
+}
+static int sweep_block_size(const WsLayout& lay) {
+    int ks = sb_pick_ks((int)lay.L, (int)lay.d, (int)lay.P, (int)lay.wd, sweep_smem_budget());
+    const char* env = getenv("BARK_SWEEP_KB");  // testing: force a smaller block
+    if (env && ks > 0) {
+        const int k = atoi(env);
+        if ((k == 1 || k == 2 || k == 4 || k == 8) && k <= ks) ks = k;
+    }
+    return ks;
+}
+static void sweep_launch_config(cudaLaunchConfig_t* cfg, cudaLaunchAttribute* attr, int64_t chains, int R, size_t smem,
+                                cudaStream_t st) {
+    *cfg = cudaLaunchConfig_t{};
+    cfg->gridDim = dim3((unsigned)(chains * R));
+    cfg->blockDim = dim3(SB_THREADS);
+    cfg->dynamicSmemBytes = smem;
+    cfg->stream = st;
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)R;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg->attrs = attr;
+    cfg->numAttrs = 1;
+}
+static int pick_cluster_size(int64_t chains, size_t smem) {
     int dev = 0, sms = 148;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const char* env = getenv("BARK_SWEEP_CLUSTER");
-    if (env) {
-        const int r = atoi(env);
-        if (r == 1 || r == 2 || r == 4) return r;
-    }
     int R = 1;
-    while (R < SW_MAX_R && chains * (R * 2) <= sms) R *= 2;
+    const char* env = getenv("BARK_SWEEP_CLUSTER");
+    const int forced = env ? atoi(env) : 0;
+    if (forced == 1 || forced == 2 || forced == 4 || forced == 8 || forced == 16) {
+        R = forced;
+    } else {
+        while (R < SB_MAX_R && chains * (R * 2) <= sms) R *= 2;
+    }
+    // every chain's cluster should be resident at once; the driver knows how many clusters of this size fit
+    while (R > 1) {
+        cudaLaunchConfig_t cfg;
+        cudaLaunchAttribute attr[1];
+        sweep_launch_config(&cfg, attr, chains, R, smem, nullptr);
+        int nclusters = 0;
+        const cudaError_t e = cudaOccupancyMaxActiveClusters(&nclusters, sweep_block_kernel, &cfg);
+        if (e == cudaSuccess && (nclusters >= chains || forced)) break;
+        if (e != cudaSuccess) cudaGetLastError();  // e.g. cluster size not supported: clear and try a smaller one
+        R /= 2;
+    }
     return R;
 }
 
@@ -484,34 +526,32 @@ static cudaError_t launch_hyper(cudaStream_t st, const WsLayout& lay, void* ws, 
     return cudaLaunchKernelEx(&cfg, hyper_refresh_kernel, lay, ws);
 }
 
-static size_t sweep_smem_budget() {
-    int dev = 0, optin = 227 * 1024;
-    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-    return (size_t)std::min(optin, 227 * 1024);
+struct SweepGeom {
+    int R, ks;
+    size_t smem;
+};
+// 0 on success; the geometry depends only on the dimensions, so it is computed once per C-ABI call
+static cudaError_t sweep_geometry(const WsLayout& lay, SweepGeom* g) {
+    g->ks = sweep_block_size(lay);
+    if (g->ks <= 0) return cudaErrorInvalidValue;
+    g->smem = sb_layout((int)lay.L, (int)lay.d, (int)lay.P, (int)lay.wd, g->ks).total;
+    cudaError_t e = cudaFuncSetAttribute(sweep_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g->smem);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(sweep_block_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    if (e != cudaSuccess) return e;
+    g->R = pick_cluster_size(lay.chains, g->smem);
+    return cudaSuccess;
 }
 
-static cudaError_t launch_sweep_trees(int R, cudaStream_t st, const WsLayout& lay, void* ws, bark_nodes_soa forest,
-                                      const bark_params& prm, int64_t sidx, int64_t n_sweeps, uint64_t seed,
-                                      int64_t chain_offset, int64_t sweep_offset, const double* tape, double* trace) {
-    const size_t budget = sweep_smem_budget();
-    const SweepSmemLayout sl = sweep_smem_layout((int)lay.L, (int)lay.d, (int)lay.P, (int)lay.wd, budget);
-    if (sl.total > budget) return cudaErrorInvalidValue;
-    cudaError_t e = cudaFuncSetAttribute(sweep_trees_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sl.total);
-    if (e != cudaSuccess) return e;
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)(lay.chains * R));
-    cfg.blockDim = dim3(SW_THREADS);
-    cfg.dynamicSmemBytes = sl.total;
-    cfg.stream = st;
+static cudaError_t launch_sweep_trees(const SweepGeom& g, cudaStream_t st, const WsLayout& lay, void* ws,
+                                      bark_nodes_soa forest, const bark_params& prm, int64_t sidx, int64_t n_sweeps,
+                                      uint64_t seed, int64_t chain_offset, int64_t sweep_offset, const double* tape,
+                                      double* trace) {
+    cudaLaunchConfig_t cfg;
     cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = (unsigned)R;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, sweep_trees_kernel, lay, ws, forest, prm, sidx, n_sweeps, seed, chain_offset,
-                              sweep_offset, tape, trace, budget);
+    sweep_launch_config(&cfg, attr, lay.chains, g.R, g.smem, st);
+    return cudaLaunchKernelEx(&cfg, sweep_block_kernel, lay, ws, forest, prm, sidx, n_sweeps, seed, chain_offset,
+                              sweep_offset, tape, trace, g.ks);
 }
 
 }  // namespace bark
@@ -523,6 +563,19 @@ extern "C" {
 size_t bark_mcmc_workspace_bytes(const bark_mcmc_dims* dims) {
     if (!check_dims(dims)) return 0;
     return make_layout(*dims).total;
+}
+
+int64_t bark_mcmc_max_p_cap(const bark_mcmc_dims* dims) {
+    if (!dims || dims->n < 1 || dims->d < 1 || dims->node_limit < 3) return 0;
+    bark_mcmc_dims dm = *dims;
+    int64_t best = 0;
+    for (int64_t p = 64; p <= 8192; p += 64) {
+        dm.p_cap = p;
+        if (!check_dims(&dm)) continue;
+        const WsLayout lay = make_layout(dm);
+        if (sb_pick_ks((int)lay.L, (int)lay.d, (int)lay.P, (int)lay.wd, 227 * 1024) > 0) best = p;
+    }
+    return best;
 }
 
 int bark_mcmc_init(const bark_mcmc_dims* dims, void* workspace, bark_nodes_soa forest, const double* X,
@@ -557,16 +610,13 @@ int bark_mcmc_sweeps(const bark_mcmc_dims* dims, void* workspace, bark_nodes_soa
     BARK_CHECK_ARG(n_sweeps >= 0, "n_sweeps < 0");
     const WsLayout lay = make_layout(*dims);
     cudaStream_t st = (cudaStream_t)stream;
-    {
-        const size_t budget = sweep_smem_budget();
-        BARK_CHECK_ARG(sweep_smem_layout((int)lay.L, (int)lay.d, (int)lay.P, (int)lay.wd, budget).total <= budget,
-                       "p_cap / n / d too large for the sweep kernel's shared memory");
-    }
+    BARK_CHECK_ARG(sweep_block_size(lay) > 0, "p_cap / n / d too large for the sweep kernel's shared memory");
     BARK_CUDA(cudaFuncSetAttribute(hyper_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(la::Smem)));
     BARK_CUDA(cudaFuncSetAttribute(hyper_refresh_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(la::Smem)));
-    const int R = pick_cluster_size(dims->chains);
+    SweepGeom geom;
+    BARK_CUDA(sweep_geometry(lay, &geom));
     for (int64_t sidx = 0; sidx < n_sweeps; ++sidx) {
-        BARK_CUDA(launch_sweep_trees(R, st, lay, workspace, forest, *params, sidx, n_sweeps, seed, chain_offset,
+        BARK_CUDA(launch_sweep_trees(geom, st, lay, workspace, forest, *params, sidx, n_sweeps, seed, chain_offset,
                                      sweep_offset, tape, trace));
         BARK_CUDA(launch_hyper(st, lay, workspace, *params, sidx, n_sweeps, seed, chain_offset, sweep_offset, tape, trace));
     }
@@ -582,19 +632,16 @@ int bark_mcmc_sweeps_timed(const bark_mcmc_dims* dims, void* workspace, bark_nod
     BARK_CHECK_ARG(n_sweeps >= 1 && n_sweeps <= 4096, "n_sweeps out of range (1..4096)");
     const WsLayout lay = make_layout(*dims);
     cudaStream_t st = (cudaStream_t)stream;
-    {
-        const size_t budget = sweep_smem_budget();
-        BARK_CHECK_ARG(sweep_smem_layout((int)lay.L, (int)lay.d, (int)lay.P, (int)lay.wd, budget).total <= budget,
-                       "p_cap / n / d too large for the sweep kernel's shared memory");
-    }
+    BARK_CHECK_ARG(sweep_block_size(lay) > 0, "p_cap / n / d too large for the sweep kernel's shared memory");
     BARK_CUDA(cudaFuncSetAttribute(hyper_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(la::Smem)));
     BARK_CUDA(cudaFuncSetAttribute(hyper_refresh_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(la::Smem)));
-    const int R = pick_cluster_size(dims->chains);
+    SweepGeom geom;
+    BARK_CUDA(sweep_geometry(lay, &geom));
     std::vector<cudaEvent_t> ev((size_t)n_sweeps * 3);
     for (auto& e : ev) BARK_CUDA(cudaEventCreate(&e));
     for (int64_t sidx = 0; sidx < n_sweeps; ++sidx) {
         BARK_CUDA(cudaEventRecord(ev[sidx * 3 + 0], st));
-        BARK_CUDA(launch_sweep_trees(R, st, lay, workspace, forest, *params, sidx, n_sweeps, seed, chain_offset,
+        BARK_CUDA(launch_sweep_trees(geom, st, lay, workspace, forest, *params, sidx, n_sweeps, seed, chain_offset,
                                      sweep_offset, nullptr, nullptr));
         BARK_CUDA(cudaEventRecord(ev[sidx * 3 + 1], st));
         BARK_CUDA(launch_hyper(st, lay, workspace, *params, sidx, n_sweeps, seed, chain_offset, sweep_offset, nullptr, nullptr));

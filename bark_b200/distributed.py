@@ -68,11 +68,13 @@ def run_bark_sampler_distributed(model, data, domain, params, *, seed: int, grou
     rank, world = _world(group)
     forest, noise, scale = model
     total = forest.shape[0]
+    if total < world:  # checked on EVERY rank before any collective, so that all ranks raise together
+        raise ValueError(f"more ranks ({world}) than chains ({total})")
     lo, hi = shard_bounds(total, rank, world)
-    if hi == lo:
-        raise ValueError("more ranks than chains")
     p = copy.copy(params)
     p.num_chains = hi - lo
+    if kw.get("tape") is not None:  # a replay tape covers all chains: this rank replays its own slice
+        kw = dict(kw, tape=np.ascontiguousarray(np.asarray(kw["tape"])[lo:hi]))
     dev = torch.device("cuda", torch.cuda.current_device())
     ns, no, sc = run_bark_sampler((np.ascontiguousarray(forest[lo:hi]), np.reshape(noise, -1)[lo:hi],
                                    np.reshape(scale, -1)[lo:hi]), data, domain, p, seed=seed, chain_offset=lo,

@@ -43,11 +43,19 @@ class BARKTrainParams:
 BARKTrainParamsNumba = BARKTrainParams  # the reference's name
 
 
-def default_p_cap(m: int, node_limit: int) -> int:
-    """Leaf-column capacity: 4 leaves per tree on average (posterior forests have 1.4-2.7), multiple of 64.
-    `run_bark_sampler` doubles it and re-runs (same seed, same trajectory) if a chain ever needs more."""
+def max_p_cap(n: int, d: int, m: int, node_limit: int) -> int:
+    """Largest leaf-column capacity the sweep kernel's shared-memory working set allows for this problem size
+    (asked of the library: `bark_mcmc_max_p_cap`); the default capacity and the overflow retry are clamped to it."""
+    dims = _lib.McmcDims(1, int(n), int(d), int(m), int(node_limit), 64)
+    return int(_lib.load().bark_mcmc_max_p_cap(C.byref(dims)))
+
+
+def default_p_cap(m: int, node_limit: int, limit: int = 8192) -> int:
+    """Leaf-column capacity: 4 leaves per tree on average (posterior forests have 1.4-2.7), multiple of 64, at most
+    `limit` (see `max_p_cap`).  `run_bark_sampler` doubles it and re-runs (same seed, same trajectory) if a chain ever
+    needs more."""
     cap = min(m * ((node_limit + 1) // 2), max(4 * m, 128))
-    return min(8192, ((cap + 63) // 64) * 64)
+    return max(64, min(limit, ((cap + 63) // 64) * 64))
 
 
 def raise_for_status(status: np.ndarray):
@@ -78,7 +86,7 @@ class ChainState:
         self.chains, self.m, self.L = forest.shape
         X = np.ascontiguousarray(X, dtype=np.float64)
         self.n, self.d = X.shape
-        self.p_cap = int(p_cap) if p_cap else default_p_cap(self.m, self.L)
+        self.p_cap = int(p_cap) if p_cap else default_p_cap(self.m, self.L, max_p_cap(self.n, self.d, self.m, self.L))
         self.dims = _lib.McmcDims(self.chains, self.n, self.d, self.m, self.L, self.p_cap)
         nbytes = int(self.lib.bark_mcmc_workspace_bytes(C.byref(self.dims)))
         if nbytes == 0:
@@ -152,16 +160,20 @@ def run_bark_sampler(model, data, domain, params: BARKTrainParams, *, seed=None,
     if seed is None:
         seed = int(np.random.SeedSequence().generate_state(2, dtype=np.uint32).astype(np.uint64) @ np.array([1, 2**32], dtype=np.uint64))
     forest = model[0]
-    cap = int(p_cap) if p_cap else default_p_cap(forest.shape[1], forest.shape[2])
+    n_pts, n_feat = np.shape(data[0])
+    limit = max_p_cap(n_pts, n_feat, forest.shape[1], forest.shape[2])
+    if limit <= 0:
+        raise _lib.BarkError("problem too large for the sweep kernel's shared memory (n / d / node_limit)")
+    cap = int(p_cap) if p_cap else default_p_cap(forest.shape[1], forest.shape[2], limit)
     while True:
         try:
             return _run_bark_sampler_once(model, data, domain, params, seed=seed, p_cap=cap, tape=tape,
                                           return_trace=return_trace, chain_offset=chain_offset, device=device,
                                           return_info=return_info)
         except _ColumnOverflow:
-            if cap >= 8192:
-                raise _lib.BarkError("leaf-column capacity exceeded at p_cap=8192")
-            cap = min(8192, cap * 2)
+            if cap >= limit:
+                raise _lib.BarkError(f"leaf-column capacity exceeded at p_cap={cap}, the largest this problem size allows")
+            cap = min(limit, cap * 2)
 
 
 def _run_bark_sampler_once(model, data, domain, params: BARKTrainParams, *, seed=None, p_cap=None, tape=None,

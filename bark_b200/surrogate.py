@@ -91,6 +91,7 @@ class BARKSurrogate:
         if self._posterior is None:
             _, ft = unpack_domain(self.domain)
             self._posterior = PosteriorState(self.model_as_tuple(), self.train_data, ft, X.shape[1])
+            self._posterior.check()  # NOT_SPD / column overflow at state build must not yield silent garbage
         ps = self._posterior
         cand = _as_device_f64(X, ps.state.device)
         if batched:
@@ -127,8 +128,12 @@ class BARKPriorSurrogate(BARKSurrogate):
     `fit` only stores the training data and draws `num_samples` prior forests / noise values; `predict` is the
     same GPU path as for posterior samples."""
 
-    def __init__(self, domain, *, num_samples=5, sample_seed=None, **kwargs):
-        super().__init__(domain, num_samples=num_samples, **kwargs)
+    def __init__(self, domain, *, num_samples=5, sample_seed=0, gamma_prior_shape=2.5, gamma_prior_rate=9.0, **kwargs):
+        # defaults of the reference data model (src/bofire_mixed/data_models/surrogates/bark.py:74-86):
+        # inverse-gamma(2.5, 9.0) noise prior and a fixed sample_seed=0, not the posterior surrogate's 1.5 / 5.0
+        super().__init__(domain, num_samples=num_samples, gamma_prior_shape=gamma_prior_shape,
+                         gamma_prior_rate=gamma_prior_rate, **kwargs)
+        self.sample_seed = sample_seed
         self.sample_rng = np.random.default_rng(sample_seed)
 
     def fit(self, X: np.ndarray, Y: np.ndarray):

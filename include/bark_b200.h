@@ -126,6 +126,12 @@ typedef struct bark_mcmc_dims {
 /* bytes of the opaque per-device MCMC workspace for these dims */
 size_t bark_mcmc_workspace_bytes(const bark_mcmc_dims* dims);
 
+/* Largest leaf-column capacity (multiple of 64) the sweep kernel's shared-memory working set allows for these
+ * n / d / node_limit (p_cap and chains of `dims` are ignored); 0 if none.  The host side clamps its default and its
+ * overflow retry (the analogue of the reference's fixed node container, src/bark/fitting/tree_proposals.py:45-58)
+ * to this value. */
+int64_t bark_mcmc_max_p_cap(const bark_mcmc_dims* dims);
+
 /* Build chain state from (forest, noise, scale): leaf bitsets, leaf co-occurrence counts, B^-1, log-MLL.
  * X (n,d) row-major f64, y (n) f64, bounds (d,2) f64, feat_types (d) i32, noise/scale (chains) f64. */
 int bark_mcmc_init(const bark_mcmc_dims* dims, void* workspace, bark_nodes_soa forest, const double* X,

@@ -4,8 +4,11 @@ TEST INFRASTRUCTURE ONLY.  This module exists so that, in the build container
 (where `/root/reference` is mounted read-only), the oracle restatement in
 `oracle/bark_oracle.py` can be validated against the reference's own numba
 functions and golden vectors can be generated (`oracle/make_golden.py`).
-Nothing on the product path, in `-m gpu` tests, in `smoke()` or in `bench.py`
-imports it: `/root/reference` does not exist on the GPU box.
+Nothing on the product path, in `-m gpu` tests or in `smoke()` imports it.
+`bench.py`'s CPU legs (`--impl reference`, `cpu_baseline`) use it to time the
+reference's own sampler: on the GPU box `/root/reference` does not exist, so the
+shim then resolves to the byte-identical copy staged by `oracle/build_ref.py`
+under `baseline/_ref/src` (git-ignored, shipped by gpurun).
 
 What is shimmed (the reference itself is untouched):
   * `bofire.*`  -- imported by `src/bark/fitting/bark_sampler.py:3` and
@@ -22,7 +25,21 @@ import os
 import sys
 import types
 
-REFERENCE_SRC = os.environ.get("BARK_REFERENCE_SRC", "/root/reference/src")
+_STAGED = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref", "src")
+
+
+def _pick_src() -> str:
+    """The mounted reference (build container) or, on the GPU box, the byte-identical copy of its hot-path modules
+    staged by `oracle/build_ref.py` under baseline/_ref/ (git-ignored, shipped by gpurun)."""
+    env = os.environ.get("BARK_REFERENCE_SRC")
+    if env:
+        return env
+    if os.path.isdir("/root/reference/src/bark"):
+        return "/root/reference/src"
+    return _STAGED
+
+
+REFERENCE_SRC = _pick_src()
 
 
 def available() -> bool:

@@ -185,3 +185,29 @@ def test_new_entry_points_also_refuse_to_run_without_cuda():
     assert sur.forest.shape == (2, 3, 100)  # drawing from the prior is host code, as in the reference
     with pytest.raises(_lib.BarkError):
         sur.predict(X)
+
+
+def test_prior_surrogate_defaults_match_reference_data_model():
+    """BARKPriorSurrogate keeps ITS OWN defaults (src/bofire_mixed/data_models/surrogates/bark.py:74-86):
+    inverse-gamma(2.5, 9.0) noise prior, sample_seed 0 -> reproducible draws; the posterior surrogate keeps 1.5 / 5.0."""
+    dom = (np.array([[0.0, 1.0], [0.0, 1.0]]), np.array([2, 2]))
+    pr = bark_b200.BARKPriorSurrogate(dom)
+    assert (pr.gamma_prior_shape, pr.gamma_prior_rate, pr.sample_seed, pr.num_samples) == (2.5, 9.0, 0, 5)
+    assert (pr.alpha, pr.beta, pr.num_trees) == (0.95, 2.0, 50)
+    po = bark_b200.BARKSurrogate(dom)
+    assert (po.gamma_prior_shape, po.gamma_prior_rate) == (1.5, 5.0)
+    X, y = np.random.default_rng(0).random((6, 2)), np.arange(6.0)[:, None]
+    a = bark_b200.BARKPriorSurrogate(dom, num_trees=4).fit(X, y)
+    b = bark_b200.BARKPriorSurrogate(dom, num_trees=4).fit(X, y)
+    assert a.forest.tobytes() == b.forest.tobytes() and np.array_equal(a.noise, b.noise)
+
+
+def test_distributed_sampler_rejects_more_ranks_than_chains_on_every_rank(monkeypatch):
+    """`total < world` is checked before sharding, so no rank is left waiting in the all-gather."""
+    from bark_b200 import distributed as D
+    f = bark_b200.create_empty_forest(3)[None]
+    for rank in (0, 1, 2):
+        monkeypatch.setattr(D, "_world", lambda group=None, r=rank: (r, 3))
+        with pytest.raises(ValueError, match="more ranks"):
+            D.run_bark_sampler_distributed((np.tile(f, (2, 1, 1)), np.ones(2), np.ones(2)), (None, None), None,
+                                           sampler.BARKTrainParams(num_chains=2), seed=1)
