@@ -58,6 +58,10 @@ SIGNATURES = {
     "bark_kinv_export": (c_int, [C.POINTER(McmcDims), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "bark_mcmc_sweeps": (c_int, [C.POINTER(McmcDims), c_void_p, NodesSoA, C.POINTER(Params), c_int64, c_uint64,
                                  c_int64, c_int64, c_void_p, c_void_p, c_void_p]),
+    "bark_mcmc_sweeps_ex": (c_int, [C.POINTER(McmcDims), c_void_p, NodesSoA, C.POINTER(Params), c_int64, c_uint64,
+                                    c_int64, c_int64, c_void_p, c_void_p, c_int32, c_void_p]),
+    "bark_mcmc_sweeps_timed3": (c_int, [C.POINTER(McmcDims), c_void_p, NodesSoA, C.POINTER(Params), c_int64, c_uint64,
+                                        c_int64, c_int64, C.POINTER(C.c_float), c_void_p]),
     "bark_mcmc_sweeps_timed": (c_int, [C.POINTER(McmcDims), c_void_p, NodesSoA, C.POINTER(Params), c_int64, c_uint64,
                                        c_int64, c_int64, C.POINTER(C.c_float), C.POINTER(C.c_float), c_void_p]),
     "bark_mcmc_read": (c_int, [C.POINTER(McmcDims), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,

@@ -212,7 +212,7 @@ chain_init_kernel(WsLayout lay, void* ws, bark_nodes_soa forest, const double* _
         sc->scale = scale[chain];
         sc->sig = sig;
         sc->c = c;
-        sc->q = q;
+        sc->res = yy - q;
         sc->ldt = ldt;
         sc->yy = yy;
         sc->mll = mll_from(yy, q, sig, (double)n, ldt);
@@ -232,7 +232,21 @@ chain_init_kernel(WsLayout lay, void* ws, bark_nodes_soa forest, const double* _
 //                        refreshes K^-1 at the same point, :276-282)
 // =====================================================================================================
 constexpr int HYPER_CLUSTER = 8;
-constexpr int HYPER_REFRESH_EVERY = 8;  // sweeps between forced exact refreshes (0 = only on accept; replay mode)
+constexpr int HYPER_REFRESH_EVERY = 8;  // sweeps between forced exact refreshes (0 = only on accept, as the reference)
+
+// Forced exact refresh of the running state (B^-1, w, residual, log-det) every `refresh_every` sweeps, staggered over
+// the chains; more often for an ill-conditioned B = c I + Z^T Z (cond <= (c + n) / c), whose rank-2 updates drift
+// faster and whose log-MLL amplifies the drift by 1 / sig: the period shrinks in proportion once the bound passes
+// REFRESH_COND, down to every sweep (measured: running vs from-scratch log-MLL 2e-10 at cond 500 with the period 8,
+// 1.7e-9 at cond 2000 -- tests/test_gpu_parity.py::test_running_mll_stays_within_1e9_at_low_noise).
+constexpr double REFRESH_COND = 500.0;
+__device__ __forceinline__ bool refresh_due(int refresh_every, double n, double c, int64_t tick) {
+    if (refresh_every <= 0) return false;
+    const double cond = (n + c) / c;
+    int every = refresh_every;
+    if (cond > REFRESH_COND) every = max(1, (int)((double)refresh_every * REFRESH_COND / cond));
+    return (tick % every) == 0;
+}
 
 __global__ void __launch_bounds__(la::THREADS, 1)
 hyper_eval_kernel(WsLayout lay, void* ws, bark_params prm, int64_t sweep_in_call, int64_t n_sweeps_call, uint64_t seed,
@@ -313,7 +327,7 @@ hyper_eval_kernel(WsLayout lay, void* ws, bark_params prm, int64_t sweep_in_call
             sc->prop_scale = hp.scale;
             sc->hyper_accept = 1;
             sc->counters[4] += 1ull;
-        } else if (refresh_every > 0 && ((sweep_offset + sweep_in_call + 1 + chain_offset + chain) % refresh_every) == 0) {
+        } else if (refresh_due(refresh_every, (double)n, sc->c, sweep_offset + sweep_in_call + 1 + chain_offset + chain)) {
             // periodic exact refresh of the running state, staggered over the chains so that every launch of the
             // refresh kernel carries about chains / refresh_every clusters (bounds the drift of the rank-2 updates between accepted
             // noise/scale moves; the reference only refreshes on accept, bark_sampler.py:276-282)
@@ -365,7 +379,7 @@ hyper_refresh_kernel(WsLayout lay, void* ws) {
         if (tid == 0) {
             const double ldt = logdet_f - (double)ph * log(c2);
             sc->noise = noise; sc->scale = scale; sc->sig = sig2; sc->c = c2;
-            sc->q = q; sc->ldt = ldt;
+            sc->res = sc->yy - q; sc->ldt = ldt;
             sc->mll = mll_from(sc->yy, q, sig2, (double)n, ldt);
             sc->hyper_accept = 0;
         }
@@ -460,7 +474,17 @@ static void sweep_launch_config(cudaLaunchConfig_t* cfg, cudaLaunchAttribute* at
     cfg->attrs = attr;
     cfg->numAttrs = 1;
 }
-static int pick_cluster_size(int64_t chains, size_t smem) {
+using SweepKernel = void (*)(WsLayout, SbLayout, void*, bark_nodes_soa, bark_params, int64_t, int64_t, uint64_t, int64_t,
+                             int64_t, const double*, double*);
+static SweepKernel sweep_kernel_for(int ks) {
+    switch (ks) {
+        case 8: return sweep_block_kernel<8>;
+        case 4: return sweep_block_kernel<4>;
+        case 2: return sweep_block_kernel<2>;
+        default: return sweep_block_kernel<1>;
+    }
+}
+static int pick_cluster_size(int64_t chains, size_t smem, SweepKernel kern) {
     int dev = 0, sms = 148;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     int R = 1;
@@ -477,7 +501,7 @@ static int pick_cluster_size(int64_t chains, size_t smem) {
         cudaLaunchAttribute attr[1];
         sweep_launch_config(&cfg, attr, chains, R, smem, nullptr);
         int nclusters = 0;
-        const cudaError_t e = cudaOccupancyMaxActiveClusters(&nclusters, sweep_block_kernel, &cfg);
+        const cudaError_t e = cudaOccupancyMaxActiveClusters(&nclusters, kern, &cfg);
         if (e == cudaSuccess && (nclusters >= chains || forced)) break;
         if (e != cudaSuccess) cudaGetLastError();  // e.g. cluster size not supported: clear and try a smaller one
         R /= 2;
@@ -487,7 +511,7 @@ static int pick_cluster_size(int64_t chains, size_t smem) {
 
 static cudaError_t launch_hyper(cudaStream_t st, const WsLayout& lay, void* ws, const bark_params& prm, int64_t sidx,
                                 int64_t n_sweeps, uint64_t seed, int64_t chain_offset, int64_t sweep_offset,
-                                const double* tape, double* trace) {
+                                const double* tape, double* trace, int refresh_every, cudaEvent_t mid = nullptr) {
     {
         // forward sweep: as many CTAs per chain (1, 2 or 4) as fit on the GPU in one wave
         int dev = 0, sms = 148;
@@ -506,9 +530,12 @@ static cudaError_t launch_hyper(cudaStream_t st, const WsLayout& lay, void* ws, 
         eattr[0].val.clusterDim.z = 1;
         ecfg.attrs = eattr;
         ecfg.numAttrs = 1;
-        const int refresh_every = tape ? 0 : HYPER_REFRESH_EVERY;
         cudaError_t e = cudaLaunchKernelEx(&ecfg, hyper_eval_kernel, lay, ws, prm, sidx, n_sweeps, seed, chain_offset,
                                            sweep_offset, tape, trace, refresh_every);
+        if (e != cudaSuccess) return e;
+    }
+    if (mid) {
+        const cudaError_t e = cudaEventRecord(mid, st);
         if (e != cudaSuccess) return e;
     }
     cudaLaunchConfig_t cfg = {};
@@ -529,17 +556,21 @@ static cudaError_t launch_hyper(cudaStream_t st, const WsLayout& lay, void* ws, 
 struct SweepGeom {
     int R, ks;
     size_t smem;
+    SbLayout sl;
+    SweepKernel kern;
 };
 // 0 on success; the geometry depends only on the dimensions, so it is computed once per C-ABI call
 static cudaError_t sweep_geometry(const WsLayout& lay, SweepGeom* g) {
     g->ks = sweep_block_size(lay);
     if (g->ks <= 0) return cudaErrorInvalidValue;
-    g->smem = sb_layout((int)lay.L, (int)lay.d, (int)lay.P, (int)lay.wd, g->ks).total;
-    cudaError_t e = cudaFuncSetAttribute(sweep_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g->smem);
+    g->sl = sb_layout((int)lay.L, (int)lay.d, (int)lay.P, (int)lay.wd, g->ks);
+    g->smem = g->sl.total;
+    g->kern = sweep_kernel_for(g->ks);
+    cudaError_t e = cudaFuncSetAttribute((const void*)g->kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g->smem);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(sweep_block_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    e = cudaFuncSetAttribute((const void*)g->kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
     if (e != cudaSuccess) return e;
-    g->R = pick_cluster_size(lay.chains, g->smem);
+    g->R = pick_cluster_size(lay.chains, g->smem, g->kern);
     return cudaSuccess;
 }
 
@@ -550,8 +581,8 @@ static cudaError_t launch_sweep_trees(const SweepGeom& g, cudaStream_t st, const
     cudaLaunchConfig_t cfg;
     cudaLaunchAttribute attr[1];
     sweep_launch_config(&cfg, attr, lay.chains, g.R, g.smem, st);
-    return cudaLaunchKernelEx(&cfg, sweep_block_kernel, lay, ws, forest, prm, sidx, n_sweeps, seed, chain_offset,
-                              sweep_offset, tape, trace, g.ks);
+    return cudaLaunchKernelEx(&cfg, g.kern, lay, g.sl, ws, forest, prm, sidx, n_sweeps, seed, chain_offset, sweep_offset,
+                              tape, trace);
 }
 
 }  // namespace bark
@@ -605,9 +636,17 @@ int bark_mcmc_init_ex(const bark_mcmc_dims* dims, void* workspace, bark_nodes_so
 int bark_mcmc_sweeps(const bark_mcmc_dims* dims, void* workspace, bark_nodes_soa forest, const bark_params* params,
                      int64_t n_sweeps, uint64_t seed, int64_t chain_offset, int64_t sweep_offset, const double* tape,
                      double* trace, void* stream) {
+    return bark_mcmc_sweeps_ex(dims, workspace, forest, params, n_sweeps, seed, chain_offset, sweep_offset, tape, trace, -1,
+                               stream);
+}
+
+int bark_mcmc_sweeps_ex(const bark_mcmc_dims* dims, void* workspace, bark_nodes_soa forest, const bark_params* params,
+                        int64_t n_sweeps, uint64_t seed, int64_t chain_offset, int64_t sweep_offset, const double* tape,
+                        double* trace, int32_t refresh_every, void* stream) {
     BARK_CHECK_ARG(check_dims(dims), "bad dims");
     BARK_CHECK_ARG(workspace && params && forest.is_leaf, "null pointer");
     BARK_CHECK_ARG(n_sweeps >= 0, "n_sweeps < 0");
+    BARK_CHECK_ARG(refresh_every >= -1 && refresh_every <= (1 << 20), "refresh_every out of range");
     const WsLayout lay = make_layout(*dims);
     cudaStream_t st = (cudaStream_t)stream;
     BARK_CHECK_ARG(sweep_block_size(lay) > 0, "p_cap / n / d too large for the sweep kernel's shared memory");
@@ -615,10 +654,13 @@ int bark_mcmc_sweeps(const bark_mcmc_dims* dims, void* workspace, bark_nodes_soa
     BARK_CUDA(cudaFuncSetAttribute(hyper_refresh_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(la::Smem)));
     SweepGeom geom;
     BARK_CUDA(sweep_geometry(lay, &geom));
+    // default policy: forced refresh every HYPER_REFRESH_EVERY sweeps; a replayed run (tape) refreshes only on an
+    // accepted noise/scale move, exactly where the reference does (bark_sampler.py:276-282), unless told otherwise
+    const int re = (refresh_every >= 0) ? refresh_every : (tape ? 0 : HYPER_REFRESH_EVERY);
     for (int64_t sidx = 0; sidx < n_sweeps; ++sidx) {
         BARK_CUDA(launch_sweep_trees(geom, st, lay, workspace, forest, *params, sidx, n_sweeps, seed, chain_offset,
                                      sweep_offset, tape, trace));
-        BARK_CUDA(launch_hyper(st, lay, workspace, *params, sidx, n_sweeps, seed, chain_offset, sweep_offset, tape, trace));
+        BARK_CUDA(launch_hyper(st, lay, workspace, *params, sidx, n_sweeps, seed, chain_offset, sweep_offset, tape, trace, re));
     }
     BARK_LAUNCH_CHECK();
     return BARK_OK;
@@ -627,8 +669,19 @@ int bark_mcmc_sweeps(const bark_mcmc_dims* dims, void* workspace, bark_nodes_soa
 int bark_mcmc_sweeps_timed(const bark_mcmc_dims* dims, void* workspace, bark_nodes_soa forest, const bark_params* params,
                            int64_t n_sweeps, uint64_t seed, int64_t chain_offset, int64_t sweep_offset,
                            float* ms_trees_host, float* ms_hyper_host, void* stream) {
+    float ms3[3] = {0.f, 0.f, 0.f};
+    BARK_CHECK_ARG(ms_trees_host && ms_hyper_host, "null pointer");
+    const int rc = bark_mcmc_sweeps_timed3(dims, workspace, forest, params, n_sweeps, seed, chain_offset, sweep_offset, ms3, stream);
+    *ms_trees_host = ms3[0];
+    *ms_hyper_host = ms3[1] + ms3[2];
+    return rc;
+}
+
+int bark_mcmc_sweeps_timed3(const bark_mcmc_dims* dims, void* workspace, bark_nodes_soa forest, const bark_params* params,
+                            int64_t n_sweeps, uint64_t seed, int64_t chain_offset, int64_t sweep_offset, float* ms3_host,
+                            void* stream) {
     BARK_CHECK_ARG(check_dims(dims), "bad dims");
-    BARK_CHECK_ARG(workspace && params && forest.is_leaf && ms_trees_host && ms_hyper_host, "null pointer");
+    BARK_CHECK_ARG(workspace && params && forest.is_leaf && ms3_host, "null pointer");
     BARK_CHECK_ARG(n_sweeps >= 1 && n_sweeps <= 4096, "n_sweeps out of range (1..4096)");
     const WsLayout lay = make_layout(*dims);
     cudaStream_t st = (cudaStream_t)stream;
@@ -637,28 +690,31 @@ int bark_mcmc_sweeps_timed(const bark_mcmc_dims* dims, void* workspace, bark_nod
     BARK_CUDA(cudaFuncSetAttribute(hyper_refresh_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(la::Smem)));
     SweepGeom geom;
     BARK_CUDA(sweep_geometry(lay, &geom));
-    std::vector<cudaEvent_t> ev((size_t)n_sweeps * 3);
+    std::vector<cudaEvent_t> ev((size_t)n_sweeps * 4);
     for (auto& e : ev) BARK_CUDA(cudaEventCreate(&e));
     for (int64_t sidx = 0; sidx < n_sweeps; ++sidx) {
-        BARK_CUDA(cudaEventRecord(ev[sidx * 3 + 0], st));
+        BARK_CUDA(cudaEventRecord(ev[sidx * 4 + 0], st));
         BARK_CUDA(launch_sweep_trees(geom, st, lay, workspace, forest, *params, sidx, n_sweeps, seed, chain_offset,
                                      sweep_offset, nullptr, nullptr));
-        BARK_CUDA(cudaEventRecord(ev[sidx * 3 + 1], st));
-        BARK_CUDA(launch_hyper(st, lay, workspace, *params, sidx, n_sweeps, seed, chain_offset, sweep_offset, nullptr, nullptr));
-        BARK_CUDA(cudaEventRecord(ev[sidx * 3 + 2], st));
+        BARK_CUDA(cudaEventRecord(ev[sidx * 4 + 1], st));
+        BARK_CUDA(launch_hyper(st, lay, workspace, *params, sidx, n_sweeps, seed, chain_offset, sweep_offset, nullptr, nullptr,
+                               HYPER_REFRESH_EVERY, ev[sidx * 4 + 2]));
+        BARK_CUDA(cudaEventRecord(ev[sidx * 4 + 3], st));
     }
     BARK_LAUNCH_CHECK();
     BARK_CUDA(cudaStreamSynchronize(st));
-    float tt = 0.f, th = 0.f;
+    float tt = 0.f, te = 0.f, tr = 0.f;
     for (int64_t sidx = 0; sidx < n_sweeps; ++sidx) {
-        float a = 0.f, b = 0.f;
-        BARK_CUDA(cudaEventElapsedTime(&a, ev[sidx * 3 + 0], ev[sidx * 3 + 1]));
-        BARK_CUDA(cudaEventElapsedTime(&b, ev[sidx * 3 + 1], ev[sidx * 3 + 2]));
-        tt += a; th += b;
+        float a = 0.f, b = 0.f, c = 0.f;
+        BARK_CUDA(cudaEventElapsedTime(&a, ev[sidx * 4 + 0], ev[sidx * 4 + 1]));
+        BARK_CUDA(cudaEventElapsedTime(&b, ev[sidx * 4 + 1], ev[sidx * 4 + 2]));
+        BARK_CUDA(cudaEventElapsedTime(&c, ev[sidx * 4 + 2], ev[sidx * 4 + 3]));
+        tt += a; te += b; tr += c;
     }
     for (auto& e : ev) cudaEventDestroy(e);
-    *ms_trees_host = tt;
-    *ms_hyper_host = th;
+    ms3_host[0] = tt;
+    ms3_host[1] = te;
+    ms3_host[2] = tr;
     return BARK_OK;
 }
 

@@ -18,7 +18,7 @@ namespace bark {
 
 struct ChainScalars {
     double noise, scale, sig, c;
-    double q, ldt, mll, yy;
+    double res, ldt, mll, yy;  // res = y^T y - b^T Binv b (= sig * y^T K^-1 y), ldt = log|I + A/c|
     unsigned long long counters[16];
     unsigned long long phase_cycles[12];  // BARK_PHASE_TIMING builds only: per-phase clock64 totals of the tree sweep
     double prop_noise, prop_scale;  // accepted-but-not-yet-refreshed hyper proposal (hyper_eval -> hyper_refresh)

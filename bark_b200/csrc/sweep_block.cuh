@@ -62,44 +62,49 @@ struct SbAccepted {  // one accepted proposal of the current block, kept until t
 };
 struct SbCtl {
     Prop prop[SB_KB];
-    double eta[SB_KB], nu[SB_KB], uacc[SB_KB];
+    double eta[SB_KB], nu[SB_KB], luacc[SB_KB];  // luacc = log(u_accept)
     double vWv[SB_KB], vw[SB_KB];  // v_j^T Wv_j and v_j^T w of the pending proposals (refreshed after every accept)
     int G[SB_KB][SB_KB];           // g_ij = u_i^T u_j
     SbAccepted acc[SB_KB];
     int n_acc;
     int walk_from;                 // next proposal the decision walk looks at
-    int acc_slot;                  // slot accepted by the last walk, -1: block finished
+    int acc_slot;                  // slot accepted by the last walk; -1: block finished; -2: walk again
     double cw_d, cw_v;             // w update coefficients of the last accept
-    double q, ldt, mll;
+    double res, ldt, mll;  // res = y^T y - b^T Binv b (tracked directly: no cancellation against y^T y per proposal)
     int p_hi;
 };
 
+// Shared-memory plan.  V / Wd / Wv are VECTOR-major, [ks][P + 8] doubles: consecutive rows of one vector are
+// consecutive, which makes the O(P) vector passes and the DMMA fragment loads (one 16-byte load = the B operands of
+// two k-steps) bank-conflict free; the stride P + 8 (= 8 mod 16 doubles) keeps the eight vectors of a fragment load
+// on different banks.
 struct SbLayout {
-    size_t off_ctl, off_v, off_wd, off_wv, off_w, off_upos, off_uneg, off_leaf, off_u32, off_cm, off_box, off_ft,
+    unsigned off_ctl, off_v, off_wd, off_wv, off_w, off_upos, off_uneg, off_leaf, off_u32, off_cm, off_box, off_ft,
         off_logtab, off_priortab, off_used, off_red, total;
-    int ks;  // proposals per block = row stride of V / Wd / Wv
+    int ks, ps;  // proposals per block; vector stride in doubles
 };
 __host__ __device__ inline SbLayout sb_layout(int L, int d, int P, int wd, int ks) {
     SbLayout s;
     s.ks = ks;
+    s.ps = P + 8;
     size_t o = 0;
-    s.off_ctl = o;      o += align256(sizeof(SbCtl));
-    s.off_v = o;        o += align256((size_t)P * ks * 8);
-    s.off_wd = o;       o += align256((size_t)P * ks * 8);
-    s.off_wv = o;       o += align256((size_t)P * ks * 8);
-    s.off_w = o;        o += align256((size_t)P * 8);
-    s.off_upos = o;     o += align256((size_t)ks * wd * 4);
-    s.off_uneg = o;     o += align256((size_t)ks * wd * 4);
-    s.off_leaf = o;     o += align256((size_t)ks * L * 2);      // is_leaf, active
-    s.off_u32 = o;      o += align256((size_t)ks * L * 4 * 6);  // feat, left, right, parent, depth, thr
-    s.off_cm = o;       o += align256((size_t)ks * L * 2);      // leaf -> column maps
-    s.off_box = o;      o += align256((size_t)ks * d * 2 * 8);
-    s.off_ft = o;       o += align256((size_t)d * 4);
-    s.off_logtab = o;   o += align256((size_t)(L + 2) * 8);
-    s.off_priortab = o; o += align256((size_t)(L + 1) * 8);
-    s.off_used = o;     o += align256((size_t)(P / 32) * 4);
-    s.off_red = o;      o += align256((size_t)2 * 2 * SB_WARPS * SB_KB * 8);  // two buffers x two values
-    s.total = o;
+    s.off_ctl = (unsigned)o;      o += align256(sizeof(SbCtl));
+    s.off_v = (unsigned)o;        o += align256((size_t)s.ps * ks * 8);
+    s.off_wd = (unsigned)o;       o += align256((size_t)s.ps * ks * 8);
+    s.off_wv = (unsigned)o;       o += align256((size_t)s.ps * ks * 8);
+    s.off_w = (unsigned)o;        o += align256((size_t)P * 8);
+    s.off_upos = (unsigned)o;     o += align256((size_t)ks * wd * 4);
+    s.off_uneg = (unsigned)o;     o += align256((size_t)ks * wd * 4);
+    s.off_leaf = (unsigned)o;     o += align256((size_t)ks * L * 2);      // is_leaf, active
+    s.off_u32 = (unsigned)o;      o += align256((size_t)ks * L * 4 * 6);  // feat, left, right, parent, depth, thr
+    s.off_cm = (unsigned)o;       o += align256((size_t)ks * L * 2);      // leaf -> column maps
+    s.off_box = (unsigned)o;      o += align256((size_t)ks * d * 2 * 8);
+    s.off_ft = (unsigned)o;       o += align256((size_t)d * 4);
+    s.off_logtab = (unsigned)o;   o += align256((size_t)(L + 2) * 8);
+    s.off_priortab = (unsigned)o; o += align256((size_t)(L + 1) * 8);
+    s.off_used = (unsigned)o;     o += align256((size_t)(P / 32) * 4);
+    s.off_red = (unsigned)o;      o += align256((size_t)2 * 2 * SB_WARPS * 8);  // two buffers x two values per warp
+    s.total = (o > 0xFFFFFFFFull) ? 0xFFFFFFFFu : (unsigned)o;
     return s;
 }
 // Largest block size (8, 4, 2, 1) whose working set fits the shared-memory budget; 0 if not even KB = 1 does.
@@ -111,47 +116,47 @@ __host__ __device__ inline int sb_pick_ks(int L, int d, int P, int wd, size_t bu
 
 __device__ __forceinline__ double2 sb_ldcg2(const double* p) { return __ldcg(reinterpret_cast<const double2*>(p)); }
 
-// Sum of (x, y) over all threads whose slot (tid % ks) is the same; every thread receives the totals of ITS slot.
-// Deterministic (fixed shuffle tree, fixed order over the warps).  `red`: 2 * SB_WARPS * SB_KB doubles, must not be in
-// use by a reduction that other threads may still be reading (callers alternate two buffers).  One __syncthreads.
-__device__ __forceinline__ void sb_slot_sum2(double& x, double& y, int ks, double* red) {
+// Sum of (x, y) over the threads of one proposal slot (SB_THREADS / KS consecutive threads = SB_WARPS / KS whole
+// warps); every thread receives the totals of ITS slot.  Deterministic (fixed shuffle tree, fixed order over the
+// slot's warps).  `red`: 2 * SB_WARPS doubles, not in use by a reduction that other threads may still be reading
+// (callers alternate two buffers).  One __syncthreads.
+template <int KS>
+__device__ __forceinline__ void sb_slot_sum2(double& x, double& y, double* red) {
+    constexpr int WPS = SB_WARPS / KS;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    for (int o = 16; o >= ks; o >>= 1) {
-        const double tx = __shfl_xor_sync(0xffffffffu, x, o);
-        const double ty = __shfl_xor_sync(0xffffffffu, y, o);
-        x += tx;
-        y += ty;
-    }
-    if (lane < ks) {
-        red[wid * SB_KB + lane] = x;
-        red[SB_WARPS * SB_KB + wid * SB_KB + lane] = y;
+    warp_sum2(x, y);
+    if (lane == 0) {
+        red[wid] = x;
+        red[SB_WARPS + wid] = y;
     }
     __syncthreads();
-    const int j = lane & (ks - 1);
+    const int w0 = (wid / WPS) * WPS;
     double sx = 0.0, sy = 0.0;
 #pragma unroll
-    for (int w = 0; w < SB_WARPS; ++w) {
-        sx += red[w * SB_KB + j];
-        sy += red[SB_WARPS * SB_KB + w * SB_KB + j];
+    for (int w = 0; w < WPS; ++w) {
+        sx += red[w0 + w];
+        sy += red[SB_WARPS + w0 + w];
     }
     x = sx;
     y = sy;
 }
 
+template <int KS>
 __global__ void __launch_bounds__(SB_THREADS, 1)
-sweep_block_kernel(WsLayout lay, void* ws, bark_nodes_soa forest, bark_params prm, int64_t sweep_in_call,
+sweep_block_kernel(WsLayout lay, SbLayout sl, void* ws, bark_nodes_soa forest, bark_params prm, int64_t sweep_in_call,
                    int64_t n_sweeps_call, uint64_t seed, int64_t chain_offset, int64_t sweep_offset,
-                   const double* __restrict__ tape, double* __restrict__ trace, int ks) {
+                   const double* __restrict__ tape, double* __restrict__ trace) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cg::cluster_group cluster = cg::this_cluster();
     const int R = (int)cluster.num_blocks(), cr = (int)cluster.block_rank();
     auto csync = [&]() {
         if (R > 1) cluster.sync(); else __syncthreads();
     };
+    constexpr int TPS = SB_THREADS / KS;  // threads per proposal slot in the O(P) vector passes
 
     const int P = (int)lay.P, L = (int)lay.L, m = (int)lay.m, n = (int)lay.n, wd = (int)lay.wd, npad = (int)lay.npad;
     const int d = (int)lay.d;
-    const SbLayout sl = sb_layout(L, d, P, wd, ks);
+    const int PS = sl.ps;
     SbCtl* ctl = (SbCtl*)(smem_raw + sl.off_ctl);
     double* V = (double*)(smem_raw + sl.off_v);
     double* Wd = (double*)(smem_raw + sl.off_wd);
@@ -168,7 +173,7 @@ sweep_block_kernel(WsLayout lay, void* ws, bark_nodes_soa forest, bark_params pr
     double* priortab = (double*)(smem_raw + sl.off_priortab);
     uint32_t* used_s = (uint32_t*)(smem_raw + sl.off_used);
     double* red = (double*)(smem_raw + sl.off_red);
-    double* red2 = red + 2 * SB_WARPS * SB_KB;
+    double* red2 = red + 2 * SB_WARPS;
 
     const int64_t chain = blockIdx.x / R;
     ChainView cv = chain_view(lay, ws, chain);
@@ -184,11 +189,11 @@ sweep_block_kernel(WsLayout lay, void* ws, bark_nodes_soa forest, bark_params pr
     csync();
     if (status0 & (BARK_ST_COL_OVERFLOW | BARK_ST_TREE_OVERFLOW | BARK_ST_HYPER_MODE)) return;
 
-    const double sig = sc->sig, c = sc->c, yy = sc->yy;
+    const double sig = sc->sig, c = sc->c;
     const double inv_c = 1.0 / c;
     const double nlogsig = (double)n * log(sig);
     if (tid == 0) {
-        ctl->q = sc->q; ctl->ldt = sc->ldt; ctl->mll = sc->mll; ctl->p_hi = sc->p_hi;
+        ctl->res = sc->res; ctl->ldt = sc->ldt; ctl->mll = sc->mll; ctl->p_hi = sc->p_hi;
     }
     for (int e = tid; e < d; e += SB_THREADS) ftc[e] = sv.ft[e];
     for (int e = tid; e < L + 2; e += SB_THREADS) logtab[e] = log((double)e);
@@ -209,8 +214,8 @@ sweep_block_kernel(WsLayout lay, void* ws, bark_nodes_soa forest, bark_params pr
 #endif
     __syncthreads();
 
-    for (int t0 = 0; t0 < m; t0 += ks) {
-        const int nb = min(ks, m - t0);  // proposals in this block
+    for (int t0 = 0; t0 < m; t0 += KS) {
+        const int nb = min(KS, m - t0);  // proposals in this block
         SB_MARK(0);
         // ------------------------------------------------------------------ phase 0: stage the trees, propose
         for (int e = tid; e < nb * L; e += SB_THREADS) {
@@ -230,7 +235,7 @@ sweep_block_kernel(WsLayout lay, void* ws, bark_nodes_soa forest, bark_params pr
         }
         for (int e = tid; e < nb * 2 * d; e += SB_THREADS) box_all[e] = sv.bounds[e % (2 * d)];
         __syncthreads();
-        if (wid < ks) {
+        if (wid < KS) {
             const int j = wid;
             if (j < nb) {
                 double un[6];
@@ -248,14 +253,14 @@ sweep_block_kernel(WsLayout lay, void* ws, bark_nodes_soa forest, bark_params pr
                 if (lane == 0) {
                     if (pp.valid && pp.move == MOVE_GROW) pp.a = -1;  // allocated at the decision
                     ctl->prop[j] = pp;
-                    ctl->uacc[j] = un[4];
+                    ctl->luacc[j] = log(un[4]);
                 }
             } else if (lane == 0) {
                 Prop pp;
                 pp.move = 0; pp.valid = 0; pp.node = 0; pp.feat = 0; pp.thr = 0.f; pp.sl = 0; pp.sr = 0; pp.a = 0; pp.b = 0;
                 pp.lqp = -INFINITY; pp.depth = 0; pp.pad = 0;
                 ctl->prop[j] = pp;
-                ctl->uacc[j] = 1.0;
+                ctl->luacc[j] = 0.0;
             }
         }
         if (tid == 0) { ctl->n_acc = 0; ctl->walk_from = 0; }
@@ -267,82 +272,98 @@ sweep_block_kernel(WsLayout lay, void* ws, bark_nodes_soa forest, bark_params pr
 
         // ------------------------------------------------------------------ Wd = Binv (e_a - e_b): symmetric rows
         // (issued before the masks so that the gathers overlap them; a grow's e_a / c term is added at its decision)
-        for (int idx = tid; idx < E * ks; idx += SB_THREADS) {
-            const int k = idx / ks, j = idx - k * ks;
-            double val = 0.0;
-            if (j < nb && ctl->prop[j].valid) {
-                const int a = ctl->prop[j].a, b = ctl->prop[j].b;
-                const double sb = __ldcg(cv.Binv + ((k <= b) ? ((size_t)b * P + k) : ((size_t)k * P + b)));
-                const double sa = (a >= 0) ? __ldcg(cv.Binv + ((k <= a) ? ((size_t)a * P + k) : ((size_t)k * P + a))) : 0.0;
-                val = sa - sb;
+        {
+            int ga[KS], gb[KS];
+#pragma unroll
+            for (int j = 0; j < KS; ++j) {
+                const bool ok = j < nb && ctl->prop[j].valid;
+                ga[j] = ok ? ctl->prop[j].a : -1;
+                gb[j] = ok ? ctl->prop[j].b : -1;
             }
-            Wd[idx] = val;
+            for (int k = tid; k < E; k += SB_THREADS) {
+                double sa[KS], sb[KS];
+#pragma unroll
+                for (int j = 0; j < KS; ++j) {  // all gathers in flight before the first shared-memory store
+                    const int a = ga[j], b = gb[j];
+                    sa[j] = sb[j] = 0.0;
+                    if (b >= 0) sb[j] = __ldcg(cv.Binv + ((k <= b) ? ((size_t)b * P + k) : ((size_t)k * P + b)));
+                    if (a >= 0) sa[j] = __ldcg(cv.Binv + ((k <= a) ? ((size_t)a * P + k) : ((size_t)k * P + a)));
+                }
+#pragma unroll
+                for (int j = 0; j < KS; ++j) Wd[(size_t)j * PS + k] = sa[j] - sb[j];
+            }
         }
 
         // ------------------------------------------------------------------ phase 1: moved-point masks, eta, n_u
+        // SB_WARPS / KS warps per proposal; a warp takes every (SB_WARPS / KS)-th 32-point word of its proposal.  The
+        // leaf bitsets come in coalesced (one word per lane per 1024 points) and are handed out by shuffles.
         {
-            double eta_p[SB_KB];
-            int cnt_p[SB_KB];
-#pragma unroll
-            for (int j = 0; j < SB_KB; ++j) { eta_p[j] = 0.0; cnt_p[j] = 0; }
-            for (int w = wid; w < wd; w += SB_WARPS) {
-                const int i = w * 32 + lane;
-                const double yv = (i < n) ? sv.y[i] : 0.0;
-                uint32_t wa[SB_KB], wb[SB_KB];
-                double xv[SB_KB];
-#pragma unroll
-                for (int j = 0; j < SB_KB; ++j) {
-                    wa[j] = wb[j] = 0u;
-                    xv[j] = 0.0;
-                    if (j < nb && ctl->prop[j].valid) {
-                        const int mv = ctl->prop[j].move;
-                        wb[j] = __ldcg(cv.bits + (size_t)ctl->prop[j].b * wd + w);
-                        if (mv == MOVE_CHANGE) wa[j] = __ldcg(cv.bits + (size_t)ctl->prop[j].a * wd + w);
-                        if (mv != MOVE_PRUNE && i < n) xv[j] = sv.Xt[(size_t)ctl->prop[j].feat * npad + i];
-                    }
+            constexpr int nparts = SB_WARPS / KS;
+            const int j = wid & (KS - 1), part = wid / KS;
+            const bool live = j < nb && ctl->prop[j].valid;
+            const int mv = ctl->prop[j].move, pa = ctl->prop[j].a, pb = ctl->prop[j].b;
+            const float pthr = ctl->prop[j].thr;
+            const int pf = live ? ctl->prop[j].feat : 0;
+            const int ftype = ftc[pf];
+            const double* xf = sv.Xt + (size_t)pf * npad;
+            double eta_p = 0.0;
+            int cnt_p = 0;
+            for (int ch = 0; ch * 32 < wd; ++ch) {
+                const int wl = ch * 32 + lane;
+                uint32_t wb_l = 0u, wa_l = 0u;
+                if (live && wl < wd) {
+                    wb_l = __ldcg(cv.bits + (size_t)pb * wd + wl);
+                    if (mv == MOVE_CHANGE) wa_l = __ldcg(cv.bits + (size_t)pa * wd + wl);
                 }
+                for (int ww0 = part; ww0 < 32; ww0 += 8 * nparts) {
+                    double xv[8], yv[8];
 #pragma unroll
-                for (int j = 0; j < SB_KB; ++j) {
-                    if (j >= ks) break;
-                    bool pos = false, neg = false;
-                    if (j < nb && ctl->prop[j].valid && i < n) {
-                        const int mv = ctl->prop[j].move;
-                        const bool in_b = (wb[j] >> lane) & 1u;
-                        if (mv == MOVE_GROW) {
-                            if (in_b) pos = !goes_left(xv[j], ctl->prop[j].thr, ftc[ctl->prop[j].feat]);
-                        } else if (mv == MOVE_PRUNE) {
-                            pos = in_b;
-                        } else {  // change: b = left child's column, a = right child's column
-                            const bool in_a = (wa[j] >> lane) & 1u;
-                            if (in_a || in_b) {
-                                const bool gl = goes_left(xv[j], ctl->prop[j].thr, ftc[ctl->prop[j].feat]);
-                                pos = in_b && !gl;
-                                neg = in_a && gl;
-                            }
+                    for (int u = 0; u < 8; ++u) {
+                        const int ww = ww0 + u * nparts, i = (ch * 32 + ww) * 32 + lane;
+                        xv[u] = yv[u] = 0.0;
+                        if (live && ww < 32 && i < n) {
+                            yv[u] = sv.y[i];
+                            if (mv != MOVE_PRUNE) xv[u] = xf[i];
                         }
                     }
-                    const unsigned bp = __ballot_sync(0xffffffffu, pos), bn = __ballot_sync(0xffffffffu, neg);
-                    if (lane == 0) { upos[j * wd + w] = bp; uneg[j * wd + w] = bn; }
-                    if (pos) eta_p[j] += yv;
-                    if (neg) eta_p[j] -= yv;
-                    cnt_p[j] += __popc(bp) + __popc(bn);
-                }
-            }
-            // per-slot totals: eta (fixed tree over lanes, fixed order over warps), n_u (exact integers)
 #pragma unroll
-            for (int j = 0; j < SB_KB; ++j) {
-                if (j >= ks) break;
-                const double e = warp_sum(eta_p[j]);
-                if (lane == 0) {
-                    red[wid * SB_KB + j] = e;
-                    red[SB_WARPS * SB_KB + wid * SB_KB + j] = (double)cnt_p[j];
+                    for (int u = 0; u < 8; ++u) {
+                        const int ww = ww0 + u * nparts, w = ch * 32 + ww, i = w * 32 + lane;
+                        if (ww >= 32 || w >= wd) break;  // warp-uniform
+                        const uint32_t wbw = __shfl_sync(0xffffffffu, wb_l, ww), waw = __shfl_sync(0xffffffffu, wa_l, ww);
+                        bool pos = false, neg = false;
+                        if (live && i < n) {
+                            const bool in_b = (wbw >> lane) & 1u;
+                            if (mv == MOVE_GROW) {
+                                if (in_b) pos = !goes_left(xv[u], pthr, ftype);
+                            } else if (mv == MOVE_PRUNE) {
+                                pos = in_b;
+                            } else {  // change: b = left child's column, a = right child's column
+                                const bool in_a = (waw >> lane) & 1u;
+                                if (in_a || in_b) {
+                                    const bool gl = goes_left(xv[u], pthr, ftype);
+                                    pos = in_b && !gl;
+                                    neg = in_a && gl;
+                                }
+                            }
+                        }
+                        const unsigned bp = __ballot_sync(0xffffffffu, pos), bn = __ballot_sync(0xffffffffu, neg);
+                        if (lane == 0) { upos[j * wd + w] = bp; uneg[j * wd + w] = bn; }
+                        if (pos) eta_p += yv[u];
+                        if (neg) eta_p -= yv[u];
+                        cnt_p += __popc(bp) + __popc(bn);
+                    }
                 }
             }
+            // per-slot totals: eta (fixed tree over lanes, fixed order over the slot's warps), n_u (exact integers)
+            const double e = warp_sum(eta_p);
+            if (lane == 0) { red[wid] = e; red[SB_WARPS + wid] = (double)cnt_p; }
             __syncthreads();
-            if (tid < ks) {
-                double e = 0.0, cn = 0.0;
-                for (int w = 0; w < SB_WARPS; ++w) { e += red[w * SB_KB + tid]; cn += red[SB_WARPS * SB_KB + w * SB_KB + tid]; }
-                ctl->eta[tid] = e;
+            if (tid < KS) {
+                double es = 0.0, cn = 0.0;
+#pragma unroll
+                for (int pp = 0; pp < nparts; ++pp) { es += red[pp * KS + tid]; cn += red[SB_WARPS + pp * KS + tid]; }
+                ctl->eta[tid] = es;
                 ctl->nu[tid] = cn;
             }
         }
@@ -352,37 +373,39 @@ sweep_block_kernel(WsLayout lay, void* ws, bark_nodes_soa forest, bark_params pr
         {
             const int share = E / R;  // E is a multiple of 16 >= R
             const int r0 = cr * share, r1 = r0 + share;
-            unsigned negmask = 0, valmask = 0;
+            // a prune's u is a whole leaf, so its v is that leaf's column of the exact integer A: no scan
+            unsigned negmask = 0, valmask = 0, scanmask = 0;
             for (int j = 0; j < nb; ++j) {
                 if (ctl->prop[j].valid) {
                     valmask |= 1u << j;
+                    if (ctl->prop[j].move != MOVE_PRUNE) scanmask |= 1u << j;
                     if (ctl->prop[j].move == MOVE_CHANGE) negmask |= 1u << j;
                 }
             }
-            for (int base = r0; base < r1; base += SB_THREADS / 4) {
-                const int q = base + (tid >> 2), part = tid & 3;
-                int cnt[SB_KB];
+            const int nv4 = wd >> 2;  // 16-byte vectors per bitset (wd is a multiple of 4)
+            for (int base = r0; base < r1; base += SB_THREADS / 2) {
+                const int q = base + (tid >> 1), part = tid & 1;
+                int cnt[KS];
 #pragma unroll
-                for (int j = 0; j < SB_KB; ++j) cnt[j] = 0;
-                if (q < r1 && q < p_hi) {
-                    const uint32_t* bq = cv.bits + (size_t)q * wd;
-                    // wd is a multiple of 4: 16-byte loads, four in flight per thread
-                    for (int w0 = part * 4; w0 < wd; w0 += 64) {
+                for (int j = 0; j < KS; ++j) cnt[j] = 0;
+                if (q < r1 && q < p_hi && scanmask) {
+                    const uint4* bq = reinterpret_cast<const uint4*>(cv.bits + (size_t)q * wd);
+                    for (int v0 = part; v0 < nv4; v0 += 8) {
                         uint4 x[4];
 #pragma unroll
-                        for (int g = 0; g < 4; ++g)
-                            x[g] = (w0 + 16 * g < wd) ? __ldcg(reinterpret_cast<const uint4*>(bq + w0 + 16 * g)) : make_uint4(0, 0, 0, 0);
+                        for (int g = 0; g < 4; ++g) x[g] = (v0 + 2 * g < nv4) ? __ldcg(bq + v0 + 2 * g) : make_uint4(0, 0, 0, 0);
 #pragma unroll
                         for (int g = 0; g < 4; ++g) {
-                            if (w0 + 16 * g >= wd) break;
+                            if (v0 + 2 * g >= nv4) break;
                             if ((x[g].x | x[g].y | x[g].z | x[g].w) == 0u) continue;
+                            const int wo = (v0 + 2 * g) * 4;
 #pragma unroll
-                            for (int j = 0; j < SB_KB; ++j) {
-                                if (!((valmask >> j) & 1u)) continue;
-                                const uint4 up = *reinterpret_cast<const uint4*>(upos + j * wd + w0 + 16 * g);
+                            for (int j = 0; j < KS; ++j) {
+                                if (!((scanmask >> j) & 1u)) continue;
+                                const uint4 up = *reinterpret_cast<const uint4*>(upos + j * wd + wo);
                                 cnt[j] += __popc(x[g].x & up.x) + __popc(x[g].y & up.y) + __popc(x[g].z & up.z) + __popc(x[g].w & up.w);
                                 if ((negmask >> j) & 1u) {
-                                    const uint4 un = *reinterpret_cast<const uint4*>(uneg + j * wd + w0 + 16 * g);
+                                    const uint4 un = *reinterpret_cast<const uint4*>(uneg + j * wd + wo);
                                     cnt[j] -= __popc(x[g].x & un.x) + __popc(x[g].y & un.y) + __popc(x[g].z & un.z) + __popc(x[g].w & un.w);
                                 }
                             }
@@ -390,26 +413,26 @@ sweep_block_kernel(WsLayout lay, void* ws, bark_nodes_soa forest, bark_params pr
                     }
                 }
 #pragma unroll
-                for (int j = 0; j < SB_KB; ++j) {
-                    cnt[j] += __shfl_xor_sync(0xffffffffu, cnt[j], 1);
-                    cnt[j] += __shfl_xor_sync(0xffffffffu, cnt[j], 2);
-                }
+                for (int j = 0; j < KS; ++j) cnt[j] += __shfl_xor_sync(0xffffffffu, cnt[j], 1);
                 if (q < r1) {
-                    // the four threads of a column write its ks values (two each at ks = 8) to every CTA of the cluster
+                    // the two threads of a column write its KS values to every CTA of the cluster
 #pragma unroll
-                    for (int j = 0; j < SB_KB; ++j) {
-                        if (j < ks && (j & 3) == part) {
-                            const double val = (double)cnt[j];
-                            for (int r = 0; r < R; ++r) cluster.map_shared_rank(V, r)[(size_t)q * ks + j] = val;
+                    for (int j = 0; j < KS; ++j) {
+                        if ((j & 1) == part || KS == 1) {
+                            double val = (double)cnt[j];
+                            if (((valmask & ~scanmask) >> j) & 1u)
+                                val = (q < p_hi) ? (double)__ldcg(cv.A + (size_t)q * P + ctl->prop[j].b) : 0.0;
+                            if (KS > 1 || part == 0)
+                                for (int r = 0; r < R; ++r) cluster.map_shared_rank(V, r)[(size_t)j * PS + q] = val;
                         }
                     }
                 }
             }
             // g_ij = u_i^T u_j, i < j: one warp per pair
-            const int npair = ks * (ks - 1) / 2;
+            constexpr int npair = KS * (KS - 1) / 2;
             for (int pr = wid; pr < npair; pr += SB_WARPS) {
                 int i = 0, rem = pr;
-                while (rem >= ks - 1 - i) { rem -= ks - 1 - i; ++i; }
+                while (rem >= KS - 1 - i) { rem -= KS - 1 - i; ++i; }
                 const int j = i + 1 + rem;
                 int g = 0;
                 if (((valmask >> i) & 1u) && ((valmask >> j) & 1u)) {
@@ -429,48 +452,103 @@ sweep_block_kernel(WsLayout lay, void* ws, bark_nodes_soa forest, bark_params pr
         // ------------------------------------------------------------------ phase 3: Wv = Binv V on the FP64 tensor pipe
         // Unit I = the 8 rows [8I, 8I+8) of the result: row part (row block I of the lower triangle times V) plus
         // column part (column block I below the diagonal, transposed, times V) -- (nb8 + 1) 8x8 blocks whatever I is,
-        // so every unit costs the same.  One warp per unit; C fragment = Y[8I + lq][2 lk, 2 lk + 1].
+        // so every unit costs the same.  One warp per unit; C fragment = Y[8I + lq][2 lk, 2 lk + 1].  In both parts
+        // the k index of DMMA step s is row / column 2 lk + s of the block (any bijection of the eight works), so the B
+        // operands of the two steps are ONE 16-byte load from the vector-major V.  Eight blocks' loads are in flight
+        // at a time, four independent accumulator chains.
         for (int I = gw; I < nb8; I += ngw) {
-            double c0 = 0.0, c1 = 0.0;
+            double acc[4][2];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) acc[u][0] = acc[u][1] = 0.0;
             const int row = 8 * I + lq;
-            const bool vec_on = lq < ks;
-            const double* rowp = cv.Binv + (size_t)row * P + 2 * lk;
-            // row part: k index of step s in block kb is column 8 kb + 2 lk + s (any bijection of the 8 columns works)
-#pragma unroll 4
-            for (int kb = 0; kb <= I; ++kb) {
-                double2 x = sb_ldcg2(rowp + 8 * kb);
-                const int col = 8 * kb + 2 * lk;
-                if (kb == I) {  // diagonal block: only columns <= row are kept current
-                    if (col > row) x.x = 0.0;
-                    if (col + 1 > row) x.y = 0.0;
+            const bool vec_on = lq < KS;
+            const double2 zero2 = make_double2(0.0, 0.0);
+            const double* vp = V + (size_t)(vec_on ? lq : 0) * PS + 2 * lk;  // B operands: *(double2*)(vp + 8 * block)
+            // ---- row part, blocks 0 .. I-1 (strictly below the diagonal block): A[lq][k] = Binv[8I + lq][8 kb + 2 lk + s]
+            {
+                const double* rp = cv.Binv + (size_t)row * P + 2 * lk;
+                int kb = 0;
+                for (; kb + 8 <= I; kb += 8) {
+                    double2 x[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) x[u] = sb_ldcg2(rp + 8 * (kb + u));
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const double2 bb = vec_on ? *reinterpret_cast<const double2*>(vp + 8 * (kb + u)) : zero2;
+                        la::dmma_m8n8k4(acc[u & 3][0], acc[u & 3][1], x[u].x, bb.x);
+                        la::dmma_m8n8k4(acc[u & 3][0], acc[u & 3][1], x[u].y, bb.y);
+                    }
                 }
-                const double b0 = vec_on ? V[(size_t)col * ks + lq] : 0.0;
-                const double b1 = vec_on ? V[(size_t)(col + 1) * ks + lq] : 0.0;
-                la::dmma_m8n8k4(c0, c1, x.x, b0);
-                la::dmma_m8n8k4(c0, c1, x.y, b1);
-            }
-            // column part: A[lq][k] = Binv[8 ib + k (+4)][8I + lq], rows strictly below the diagonal
-            const double* colp = cv.Binv + (size_t)lk * P + 8 * I + lq;
-#pragma unroll 4
-            for (int ib = I; ib < nb8; ++ib) {
-                double x0 = __ldcg(colp + (size_t)(8 * ib) * P);
-                double x1 = __ldcg(colp + (size_t)(8 * ib + 4) * P);
-                if (ib == I) {
-                    if (lk <= lq) x0 = 0.0;
-                    if (lk + 4 <= lq) x1 = 0.0;
+                // remainder (fewer than eight blocks) and the diagonal block, of which only columns <= row are current
+                double2 x[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) x[u] = (kb + u <= I) ? sb_ldcg2(rp + 8 * (kb + u)) : zero2;
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    if (kb + u > I) break;
+                    if (kb + u == I) {
+                        if (2 * lk > lq) x[u].x = 0.0;
+                        if (2 * lk + 1 > lq) x[u].y = 0.0;
+                    }
+                    const double2 bb = vec_on ? *reinterpret_cast<const double2*>(vp + 8 * (kb + u)) : zero2;
+                    la::dmma_m8n8k4(acc[u & 3][0], acc[u & 3][1], x[u].x, bb.x);
+                    la::dmma_m8n8k4(acc[u & 3][0], acc[u & 3][1], x[u].y, bb.y);
                 }
-                const double b0 = vec_on ? V[(size_t)(8 * ib + lk) * ks + lq] : 0.0;
-                const double b1 = vec_on ? V[(size_t)(8 * ib + 4 + lk) * ks + lq] : 0.0;
-                la::dmma_m8n8k4(c0, c1, x0, b0);
-                la::dmma_m8n8k4(c0, c1, x1, b1);
             }
-            if (2 * lk < ks) {
-                if (ks >= 2) {
-                    const double2 out = make_double2(c0, c1);
-                    for (int r = 0; r < R; ++r)
-                        *reinterpret_cast<double2*>(cluster.map_shared_rank(Wv, r) + (size_t)row * ks + 2 * lk) = out;
-                } else {
-                    for (int r = 0; r < R; ++r) cluster.map_shared_rank(Wv, r)[row] = c0;
+            // ---- column part, blocks I (strictly lower part) .. nb8-1: A[lq][k] = Binv[8 ib + 2 lk + s][8I + lq]
+            {
+                const double* cp = cv.Binv + (size_t)(8 * I + 2 * lk) * P + 8 * I + lq;  // block ib: cp + (ib - I) * 8 P
+                const size_t bstep = (size_t)8 * P;
+                int ib = I;
+                {   // diagonal block
+                    double x0 = __ldcg(cp), x1 = __ldcg(cp + P);
+                    if (2 * lk <= lq) x0 = 0.0;
+                    if (2 * lk + 1 <= lq) x1 = 0.0;
+                    const double2 bb = vec_on ? *reinterpret_cast<const double2*>(vp + 8 * ib) : zero2;
+                    la::dmma_m8n8k4(acc[0][0], acc[0][1], x0, bb.x);
+                    la::dmma_m8n8k4(acc[0][0], acc[0][1], x1, bb.y);
+                    ++ib;
+                    cp += bstep;
+                }
+                for (; ib + 8 <= nb8; ib += 8) {
+                    double x0[8], x1[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        x0[u] = __ldcg(cp + u * bstep);
+                        x1[u] = __ldcg(cp + u * bstep + P);
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const double2 bb = vec_on ? *reinterpret_cast<const double2*>(vp + 8 * (ib + u)) : zero2;
+                        la::dmma_m8n8k4(acc[u & 3][0], acc[u & 3][1], x0[u], bb.x);
+                        la::dmma_m8n8k4(acc[u & 3][0], acc[u & 3][1], x1[u], bb.y);
+                    }
+                    cp += 8 * bstep;
+                }
+                double x0[8], x1[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    x0[u] = x1[u] = 0.0;
+                    if (ib + u < nb8) {
+                        x0[u] = __ldcg(cp + u * bstep);
+                        x1[u] = __ldcg(cp + u * bstep + P);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    if (ib + u >= nb8) break;
+                    const double2 bb = vec_on ? *reinterpret_cast<const double2*>(vp + 8 * (ib + u)) : zero2;
+                    la::dmma_m8n8k4(acc[u & 3][0], acc[u & 3][1], x0[u], bb.x);
+                    la::dmma_m8n8k4(acc[u & 3][0], acc[u & 3][1], x1[u], bb.y);
+                }
+            }
+            const double c0 = (acc[0][0] + acc[1][0]) + (acc[2][0] + acc[3][0]);
+            const double c1 = (acc[0][1] + acc[1][1]) + (acc[2][1] + acc[3][1]);
+            if (2 * lk < KS) {
+                for (int r = 0; r < R; ++r) {
+                    double* dst = cluster.map_shared_rank(Wv, r) + (size_t)(2 * lk) * PS + row;
+                    dst[0] = c0;
+                    if (2 * lk + 1 < KS) dst[PS] = c1;
                 }
             }
         }
@@ -479,142 +557,176 @@ sweep_block_kernel(WsLayout lay, void* ws, bark_nodes_soa forest, bark_params pr
         SB_MARK(6);
 
         // ------------------------------------------------------------------ phase 4: decide the proposals in order
-        // (identical on every CTA of the cluster).  Thread mapping of the O(P) vector work: slot j = tid % ks,
-        // rows k = tid / ks + (512 / ks) * it.
-        const int my_j = tid & (ks - 1);
-        const int k_first = tid / ks, k_step = SB_THREADS / ks;
+        // (identical on every CTA of the cluster).  Thread mapping of the O(P) vector work: slot my_j = tid / TPS,
+        // rows k = tid % TPS + TPS * it (consecutive threads, consecutive rows of one vector).
+        const int my_j = tid / TPS, kf = tid - my_j * TPS;
+        const double* Vj = V + (size_t)my_j * PS;
+        double* Wdj = Wd + (size_t)my_j * PS;
+        double* Wvj = Wv + (size_t)my_j * PS;
         auto refresh_scalars = [&](int from, double* buf) {  // vWv_j, vw_j for the pending slots j >= from
             double x = 0.0, y = 0.0;
             if (my_j >= from && my_j < nb) {
-                for (int k = k_first; k < E; k += k_step) {
-                    const double vv = V[(size_t)k * ks + my_j];
-                    x = fma(vv, Wv[(size_t)k * ks + my_j], x);
+                for (int k = kf; k < E; k += TPS) {
+                    const double vv = Vj[k];
+                    x = fma(vv, Wvj[k], x);
                     y = fma(vv, w_s[k], y);
                 }
             }
-            sb_slot_sum2(x, y, ks, buf);
-            if (tid < ks) { ctl->vWv[tid] = x; ctl->vw[tid] = y; }
+            sb_slot_sum2<KS>(x, y, buf);
+            if (kf == 0) { ctl->vWv[my_j] = x; ctl->vw[my_j] = y; }
         };
         refresh_scalars(0, red2);
         __syncthreads();
         while (true) {
-            if (tid == 0) {
-                // ---- the walk: scalar work per proposal (bark_sampler.py:257-264), until one is accepted
-                int j = ctl->walk_from;
-                int found = -1;
-                for (; j < nb; ++j) {
-                    Prop p = ctl->prop[j];
-                    const double cur_mll = ctl->mll;
-                    if (p.valid && p.move == MOVE_GROW) {
-                        int f = -1;
-                        for (int wq = 0; wq < P / 32 && f < 0; ++wq) {
-                            const uint32_t fr = ~used_s[wq];
-                            if (fr) f = wq * 32 + __ffs(fr) - 1;
-                        }
-                        if (f < 0 || f >= E) {
-                            // (f >= E cannot happen: E >= p_hi + nb and at most nb columns are taken per block)
-                            atomicOr(&sc->status, BARK_ST_COL_OVERFLOW);
-                            p.valid = 0;
-                            p.lqp = -INFINITY;
-                            ctl->prop[j].valid = 0;
-                        } else {
-                            p.a = f;
-                            ctl->prop[j].a = f;
-                            Wd[(size_t)f * ks + j] += inv_c;  // Binv e_f = e_f / c for a free column
-                        }
-                    }
-                    if (!p.valid) {
-                        if (trace_base && cr == 0) {
-                            trace_base[(t0 + j) * 3 + 0] = -INFINITY;
-                            trace_base[(t0 + j) * 3 + 1] = cur_mll;
-                            trace_base[(t0 + j) * 3 + 2] = 0.0;
-                        }
-                        continue;
-                    }
-                    const int a = p.a, b = p.b;
+            if (wid == 0) {
+                // ---- the walk (bark_sampler.py:257-264).  Lane j evaluates slot j against the CURRENT state; the slots
+                // up to the first accepted one are thereby decided exactly as a one-at-a-time walk would decide them
+                // (nothing changes before the first accept), the later ones are re-evaluated after the update.
+                const int from = ctl->walk_from;
+                const int j = lane;
+                const bool in_blk = j < nb;
+                const bool act = in_blk && j >= from && ctl->prop[in_blk ? j : 0].valid;
+                const double cur_mll = ctl->mll;
+                double M00 = 0.0, M01 = 0.0, M11 = 0.0, det = -1.0, Ur0 = 0.0, Ur1 = 0.0, new_res = 0.0, new_ldt = 0.0;
+                double new_mll = cur_mll, lqp = -INFINITY;
+                int a = 0, b = 0, mv = 0;
+                bool accept = false;
+                if (act) {
+                    a = ctl->prop[j].a; b = ctl->prop[j].b; mv = ctl->prop[j].move; lqp = ctl->prop[j].lqp;
+                    // a grow's column is still unallocated: Binv e_f = e_f / c, v_f = 0, w_f = 0 whichever f it will be
+                    const double Wd_a = (a >= 0) ? Wd[(size_t)j * PS + a] : inv_c;
+                    const double Wv_a = (a >= 0) ? Wv[(size_t)j * PS + a] : 0.0;
+                    const double w_a = (a >= 0) ? w_s[a] : 0.0;
                     const double eta = ctl->eta[j], n_u = ctl->nu[j];
-                    const double dWd = Wd[(size_t)a * ks + j] - Wd[(size_t)b * ks + j];
-                    const double dWv = Wv[(size_t)a * ks + j] - Wv[(size_t)b * ks + j];
-                    const double dw = w_s[a] - w_s[b];
+                    const double dWd = Wd_a - Wd[(size_t)j * PS + b];
+                    const double dWv = Wv_a - Wv[(size_t)j * PS + b];
+                    const double dw = w_a - w_s[b];
                     const double vWv = ctl->vWv[j], vw = ctl->vw[j];
-                    const double M00 = dWd, M01 = 1.0 + dWv, M11 = -n_u + vWv;
-                    const double det = M00 * M11 - M01 * M01;  // < 0 for an SPD B'
-                    const double new_ldt = ctl->ldt + log(-det);
-                    const double bq = ctl->q + 2.0 * eta * dw + eta * eta * dWd;  // b'^T Binv b'
-                    const double Ur0 = dw + eta * dWd;                            // d^T r,  r = Binv b'
-                    const double Ur1 = vw + eta * dWv;                            // v^T r
-                    const double new_q = bq - (M11 * Ur0 * Ur0 - 2.0 * M01 * Ur0 * Ur1 + M00 * Ur1 * Ur1) / det;
-                    const double new_mll = 0.5 * (-(yy - new_q) / sig - nlogsig - new_ldt);
-                    const double log_alpha = p.lqp + (new_mll - cur_mll);
-                    const bool accept = log(ctl->uacc[j]) <= fmin(log_alpha, 0.0);
-                    if (trace_base && cr == 0) {
-                        trace_base[(t0 + j) * 3 + 0] = p.lqp;
-                        trace_base[(t0 + j) * 3 + 1] = new_mll;
-                        trace_base[(t0 + j) * 3 + 2] = accept ? 1.0 : 0.0;
+                    M00 = dWd; M01 = 1.0 + dWv; M11 = -n_u + vWv;
+                    det = M00 * M11 - M01 * M01;  // < 0 for an SPD B'
+                    new_ldt = ctl->ldt + log(-det);
+                    // q = b^T Binv b changes by dq = (b'^T Binv b' - q) - [d v]^T-part; the residual y^T y - q takes -dq
+                    const double dq_b = 2.0 * eta * dw + eta * eta * dWd;  // b'^T Binv b' - b^T Binv b
+                    Ur0 = dw + eta * dWd;                                   // d^T r,  r = Binv b'
+                    Ur1 = vw + eta * dWv;                                   // v^T r
+                    new_res = ctl->res - (dq_b - (M11 * Ur0 * Ur0 - 2.0 * M01 * Ur0 * Ur1 + M00 * Ur1 * Ur1) / det);
+                    new_mll = 0.5 * (-new_res / sig - nlogsig - new_ldt);
+                    const double log_alpha = lqp + (new_mll - cur_mll);
+                    accept = ctl->luacc[j] <= fmin(log_alpha, 0.0);
+                }
+                const unsigned accm = __ballot_sync(0xffffffffu, accept);
+                int first = accm ? (__ffs(accm) - 1) : -1;
+                int f = -1;
+                if (first >= 0 && __shfl_sync(0xffffffffu, mv, first) == MOVE_GROW) {
+                    f = warp_find_free_col(used_s, P);  // lowest free column; columns pruned in this block stay reserved
+                    if (f < 0 || f >= E) {
+                        // no column left (f >= E cannot happen: E >= p_hi + nb, at most nb columns are taken per block):
+                        // the proposal becomes invalid and the walk is repeated from the same slot
+                        if (lane == first) {
+                            atomicOr(&sc->status, BARK_ST_COL_OVERFLOW);
+                            ctl->prop[j].valid = 0;
+                            ctl->acc_slot = -2;
+                        }
+                        first = -2;
                     }
-                    ++n_valid;
-                    ++n_valid_move[p.move];
-                    if (accept) {
+                }
+                if (first != -2) {
+                    const int last = (first >= 0) ? first : nb - 1;  // slots from..last are decided by this round
+                    const bool decided = in_blk && j >= from && j <= last;
+                    if (decided && trace_base && cr == 0) {
+                        trace_base[(t0 + j) * 3 + 0] = lqp;  // -inf for an invalid proposal
+                        trace_base[(t0 + j) * 3 + 1] = new_mll;
+                        trace_base[(t0 + j) * 3 + 2] = (j == first) ? 1.0 : 0.0;
+                    }
+                    const unsigned dm = __ballot_sync(0xffffffffu, decided && act);
+                    const unsigned m0 = __ballot_sync(0xffffffffu, decided && act && mv == MOVE_GROW);
+                    const unsigned m1 = __ballot_sync(0xffffffffu, decided && act && mv == MOVE_PRUNE);
+                    if (lane == 0) {
+                        n_valid += __popc(dm);
+                        n_valid_move[0] += __popc(m0);
+                        n_valid_move[1] += __popc(m1);
+                        n_valid_move[2] += __popc(dm) - __popc(m0) - __popc(m1);
+                    }
+                    const int mv_first = (first >= 0) ? __shfl_sync(0xffffffffu, mv, first) : 0;
+                    if (lane == 0 && first >= 0) {
+                        ++n_acc_tot;
+                        ++n_acc_move[mv_first];
+                    }
+                    if (first >= 0 && lane == first) {
+                        if (mv == MOVE_GROW) {
+                            a = f;
+                            ctl->prop[j].a = f;
+                            Wd[(size_t)j * PS + f] += inv_c;  // the e_f / c term of Wd = Binv (e_f - e_b)
+                            used_s[f >> 5] |= 1u << (f & 31);
+                            if (f + 1 > ctl->p_hi) ctl->p_hi = f + 1;
+                        }
                         SbAccepted& A = ctl->acc[ctl->n_acc];
                         A.al = M11 / det; A.be = -M01 / det; A.ga = M00 / det;
-                        A.eta = eta; A.nu = n_u; A.slot = j; A.a = a; A.b = b; A.move = p.move;
+                        A.eta = ctl->eta[j]; A.nu = ctl->nu[j]; A.slot = j; A.a = a; A.b = b; A.move = mv;
                         ctl->cw_d = A.al * Ur0 + A.be * Ur1;
                         ctl->cw_v = A.be * Ur0 + A.ga * Ur1;
                         ctl->n_acc += 1;
-                        ctl->q = new_q; ctl->ldt = new_ldt; ctl->mll = new_mll;
-                        if (p.move == MOVE_GROW) {
-                            used_s[a >> 5] |= 1u << (a & 31);
-                            if (a + 1 > ctl->p_hi) ctl->p_hi = a + 1;
-                        }
-                        ++n_acc_tot;
-                        ++n_acc_move[p.move];
-                        found = j;
-                        ++j;
-                        break;
+                        ctl->res = new_res; ctl->ldt = new_ldt; ctl->mll = new_mll;
+                        ctl->walk_from = j + 1;
+                        ctl->acc_slot = j;
+                    }
+                    if (first < 0 && lane == 0) {
+                        ctl->walk_from = nb;
+                        ctl->acc_slot = -1;
                     }
                 }
-                ctl->walk_from = j;
-                ctl->acc_slot = found;
             }
             __syncthreads();
             const int i = ctl->acc_slot;
+            if (i == -2) {  // a grow found no free column and was invalidated: walk again
+                __syncthreads();
+                continue;
+            }
             if (i < 0) break;
             // ---- accepted slot i: bring the pending proposals j > i, and w, up to date
             const SbAccepted A = ctl->acc[ctl->n_acc - 1];
             const int ai = A.a, bi = A.b;
+            const double* Wdi = Wd + (size_t)i * PS;
+            const double* Wvi = Wv + (size_t)i * PS;
             const bool pend = my_j > i && my_j < nb && ctl->prop[my_j].valid;
             const double g = pend ? (double)ctl->G[i][my_j] : 0.0;
-            if (tid < ks && pend && g != 0.0) {  // v_j += g d_i
-                V[(size_t)ai * ks + tid] += g;
-                V[(size_t)bi * ks + tid] -= g;
+            if (kf == 0 && pend && g != 0.0) {  // v_j += g d_i
+                V[(size_t)my_j * PS + ai] += g;
+                V[(size_t)my_j * PS + bi] -= g;
             }
             __syncthreads();
             double t0s = 0.0, t1s = 0.0;
             if (pend) {
-                for (int k = k_first; k < E; k += k_step) {
-                    const double vv = V[(size_t)k * ks + my_j];
-                    t0s = fma(Wd[(size_t)k * ks + i], vv, t0s);
-                    t1s = fma(Wv[(size_t)k * ks + i], vv, t1s);
+                for (int k = kf; k < E; k += TPS) {
+                    const double vv = Vj[k];
+                    t0s = fma(Wdi[k], vv, t0s);
+                    t1s = fma(Wvi[k], vv, t1s);
                 }
             }
-            sb_slot_sum2(t0s, t1s, ks, red);
+            sb_slot_sum2<KS>(t0s, t1s, red);
             {
                 double ddj = 0.0, dvj = 0.0;
                 if (pend) {
                     const int aj = ctl->prop[my_j].a, bj = ctl->prop[my_j].b;  // aj < 0: a grow's column, not yet allocated
-                    ddj = ((aj >= 0) ? Wd[(size_t)aj * ks + i] : 0.0) - Wd[(size_t)bj * ks + i];
-                    dvj = ((aj >= 0) ? Wv[(size_t)aj * ks + i] : 0.0) - Wv[(size_t)bj * ks + i];
+                    ddj = ((aj >= 0) ? Wdi[aj] : 0.0) - Wdi[bj];
+                    dvj = ((aj >= 0) ? Wvi[aj] : 0.0) - Wvi[bj];
                 }
                 const double cd_d = A.al * ddj + A.be * dvj, cd_v = A.be * ddj + A.ga * dvj;    // M^-1 W^T d_j
                 const double cv_d = A.al * t0s + A.be * t1s, cv_v = A.be * t0s + A.ga * t1s;    // M^-1 W^T v_j
                 const double cw_d = ctl->cw_d, cw_v = ctl->cw_v;
-                for (int k = k_first; k < E; k += k_step) {
-                    const double wd_i = Wd[(size_t)k * ks + i], wv_i = Wv[(size_t)k * ks + i];
-                    if (pend) {
-                        Wd[(size_t)k * ks + my_j] -= wd_i * cd_d + wv_i * cd_v;
-                        Wv[(size_t)k * ks + my_j] += g * wd_i - wd_i * cv_d - wv_i * cv_v;
+                if (pend) {
+                    for (int k = kf; k < E; k += TPS) {
+                        const double wd_i = Wdi[k], wv_i = Wvi[k];
+                        Wdj[k] -= wd_i * cd_d + wv_i * cd_v;
+                        Wvj[k] += g * wd_i - wd_i * cv_d - wv_i * cv_v;
                     }
-                    if (my_j == 0) w_s[k] = w_s[k] + A.eta * wd_i - wd_i * cw_d - wv_i * cw_v;  // w' = Binv' b'
+                }
+                // w' = Binv' b' (slot i's own threads are idle in this pass: they take w)
+                if (my_j == i) {
+                    for (int k = kf; k < E; k += TPS) {
+                        const double wd_i = Wdi[k], wv_i = Wvi[k];
+                        w_s[k] = w_s[k] + A.eta * wd_i - wd_i * cw_d - wv_i * cw_v;
+                    }
                 }
             }
             __syncthreads();
@@ -634,53 +746,68 @@ sweep_block_kernel(WsLayout lay, void* ws, bark_nodes_soa forest, bark_params pr
         }
         if (na > 0) {
             // Binv -= sum_s W_s M_s^-1 W_s^T on the lower triangle: C (8x8) += A (8 x 4) B (4 x 8), two accepted
-            // proposals per DMMA step.  Row blocks are paired (I, nb8-1-I) so that every unit costs nb8 + 1 blocks.
+            // proposals per DMMA step (k index = 2 * (accepted s mod 2) + component).  Row blocks are paired
+            // (I, nb8-1-I) so that every unit costs nb8 + 1 blocks; eight blocks' loads in flight, then their stores
+            // (a load -> store loop on the same array is serialised by possible aliasing).
+            constexpr int MAXST = (KS + 1) / 2;
             const int nsteps = (na + 1) >> 1;
             const int s_of = lk >> 1, comp = lk & 1;
+            // this lane's B-operand recipe per step: bfr = c1 * Wd_s[col] + c2 * Wv_s[col]; A operand = -W_s,comp[row]
+            double c1[MAXST], c2[MAXST];
+            int woff[MAXST];
             int n_prune = 0;
+#pragma unroll
+            for (int st = 0; st < MAXST; ++st) {
+                const int s = 2 * st + s_of;
+                c1[st] = c2[st] = 0.0;
+                woff[st] = 0;
+                if (s < na) {
+                    const SbAccepted& A = ctl->acc[s];
+                    c1[st] = comp ? A.be : A.al;
+                    c2[st] = comp ? A.ga : A.be;
+                    woff[st] = A.slot * PS;
+                }
+            }
             for (int s = 0; s < na; ++s) n_prune += (ctl->acc[s].move == MOVE_PRUNE);
             for (int pu = gw; pu < (nb8 + 1) / 2; pu += ngw) {
                 for (int half = 0; half < 2; ++half) {
                     const int I = half ? nb8 - 1 - pu : pu;
                     if (half && I == pu) break;
                     const int row = 8 * I + lq;
-                    double afr[SB_KB / 2];
+                    double afr[MAXST];
 #pragma unroll
-                    for (int st = 0; st < SB_KB / 2; ++st) {
-                        const int s = 2 * st + s_of;
+                    for (int st = 0; st < MAXST; ++st) {
                         afr[st] = 0.0;
-                        if (st < nsteps && s < na) {
-                            const int slot = ctl->acc[s].slot;
-                            afr[st] = -(comp ? Wv[(size_t)row * ks + slot] : Wd[(size_t)row * ks + slot]);
-                        }
+                        if (2 * st + s_of < na) afr[st] = -(comp ? Wv[woff[st] + row] : Wd[woff[st] + row]);
                     }
                     double* rowp = cv.Binv + (size_t)row * P + 2 * lk;
-#pragma unroll 2
-                    for (int J = 0; J <= I; ++J) {
-                        double2 cc = sb_ldcg2(rowp + 8 * J);
-                        const int jc = 8 * J + lq;  // B fragment column
+                    for (int J0 = 0; J0 <= I; J0 += 8) {
+                        double2 cc[8];
 #pragma unroll
-                        for (int st = 0; st < SB_KB / 2; ++st) {
-                            if (st >= nsteps) break;
-                            const int s = 2 * st + s_of;
-                            double bfr = 0.0;
-                            if (s < na) {
-                                const SbAccepted& A = ctl->acc[s];
-                                const double wdj = Wd[(size_t)jc * ks + A.slot], wvj = Wv[(size_t)jc * ks + A.slot];
-                                bfr = comp ? (A.be * wdj + A.ga * wvj) : (A.al * wdj + A.be * wvj);
+                        for (int u = 0; u < 8; ++u) cc[u] = (J0 + u <= I) ? sb_ldcg2(rowp + 8 * (J0 + u)) : make_double2(0.0, 0.0);
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) {
+                            if (J0 + u > I) break;
+                            const int jc = 8 * (J0 + u) + lq;  // B fragment column
+#pragma unroll
+                            for (int st = 0; st < MAXST; ++st) {
+                                if (st >= nsteps) break;
+                                const double bfr = c1[st] * Wd[woff[st] + jc] + c2[st] * Wv[woff[st] + jc];
+                                la::dmma_m8n8k4(cc[u].x, cc[u].y, afr[st], bfr);
                             }
-                            la::dmma_m8n8k4(cc.x, cc.y, afr[st], bfr);
-                        }
-                        if (n_prune) {  // a pruned column becomes an empty leaf: its row / column is exactly e_b / c
-                            const int col = 8 * J + 2 * lk;
-                            for (int s = 0; s < na; ++s) {
-                                if (ctl->acc[s].move != MOVE_PRUNE) continue;
-                                const int pb = ctl->acc[s].b;
-                                if (row == pb || col == pb) cc.x = (row == col) ? inv_c : 0.0;
-                                if (row == pb || col + 1 == pb) cc.y = (row == col + 1) ? inv_c : 0.0;
+                            if (n_prune) {  // a pruned column becomes an empty leaf: its row / column is exactly e_b / c
+                                const int col = 8 * (J0 + u) + 2 * lk;
+                                for (int s = 0; s < na; ++s) {
+                                    if (ctl->acc[s].move != MOVE_PRUNE) continue;
+                                    const int pb = ctl->acc[s].b;
+                                    if (row == pb || col == pb) cc[u].x = (row == col) ? inv_c : 0.0;
+                                    if (row == pb || col + 1 == pb) cc[u].y = (row == col + 1) ? inv_c : 0.0;
+                                }
                             }
                         }
-                        __stcg(reinterpret_cast<double2*>(rowp + 8 * J), cc);
+#pragma unroll
+                        for (int u = 0; u < 8; ++u)
+                            if (J0 + u <= I) __stcg(reinterpret_cast<double2*>(rowp + 8 * (J0 + u)), cc[u]);
                     }
                 }
             }
@@ -691,7 +818,7 @@ sweep_block_kernel(WsLayout lay, void* ws, bark_nodes_soa forest, bark_params pr
                 for (int s = 0; s < na; ++s) {
                     const int slot = ctl->acc[s].slot, a = ctl->acc[s].a, b = ctl->acc[s].b;
                     for (int k = r0 + tid; k < r1; k += SB_THREADS) {
-                        const int vk = (int)V[(size_t)k * ks + slot];
+                        const int vk = (int)V[(size_t)slot * PS + k];
                         if (vk != 0) {
                             atomicAdd(cv.A + (size_t)k * P + a, vk);
                             atomicAdd(cv.A + (size_t)k * P + b, -vk);
@@ -702,17 +829,18 @@ sweep_block_kernel(WsLayout lay, void* ws, bark_nodes_soa forest, bark_params pr
                 }
             }
             if (cr == 0) {
-                for (int s = 0; s < na; ++s) {
+                // one warp per accepted proposal (they edit different trees and different columns, so they are independent)
+                for (int s = wid; s < na; s += SB_WARPS) {
                     const SbAccepted A = ctl->acc[s];
                     const int a = A.a, b = A.b, slot = A.slot;
-                    // leaf bitsets (the columns of different trees are disjoint, so the order over s is free)
-                    for (int w = tid; w < wd; w += SB_THREADS) {
+                    // leaf bitsets
+                    for (int w = lane; w < wd; w += 32) {
                         const uint32_t ba = __ldcg(cv.bits + (size_t)a * wd + w), bb = __ldcg(cv.bits + (size_t)b * wd + w);
                         const uint32_t up = upos[slot * wd + w], un = uneg[slot * wd + w];
                         __stcg(cv.bits + (size_t)a * wd + w, (ba | up) & ~un);
                         __stcg(cv.bits + (size_t)b * wd + w, (bb & ~up) | un);
                     }
-                    if (tid == 0) {
+                    if (lane == 0) {
                         const Prop p = ctl->prop[slot];
                         const int nuu = (int)A.nu;  // corner term n_u d d^T
                         atomicAdd(cv.A + (size_t)a * P + a, nuu);
@@ -774,7 +902,7 @@ sweep_block_kernel(WsLayout lay, void* ws, bark_nodes_soa forest, bark_params pr
         for (int e = tid; e < P; e += SB_THREADS) cv.w[e] = w_s[e];
         for (int e = tid; e < P / 32; e += SB_THREADS) cv.colused[e] = used_s[e];
         if (tid == 0) {
-            sc->q = ctl->q; sc->ldt = ctl->ldt; sc->mll = ctl->mll; sc->p_hi = ctl->p_hi;
+            sc->res = ctl->res; sc->ldt = ctl->ldt; sc->mll = ctl->mll; sc->p_hi = ctl->p_hi;
             sc->counters[0] += (unsigned long long)m;
             sc->counters[1] += n_valid;
             sc->counters[2] += n_acc_tot;

@@ -107,11 +107,14 @@ class ChainState:
                                               _lib.INIT_SKIP_NULL if skip_null else 0, _stream()))
 
     def sweeps(self, params: BARKTrainParams, n_sweeps: int, seed: int, chain_offset=0, sweep_offset=0, tape=None,
-               trace=None):
+               trace=None, refresh_every=None):
+        """`refresh_every`: exact refresh of the running state every that many sweeps besides the refresh on every
+        accepted noise/scale move (0 = only then, as the reference; None = the library default: 8, or 0 under a tape)."""
         cp = params.to_c()
-        _lib.check(self.lib.bark_mcmc_sweeps(C.byref(self.dims), _ptr(self.ws), self.dforest.soa(), C.byref(cp),
-                                             int(n_sweeps), C.c_uint64(seed & (2**64 - 1)), int(chain_offset),
-                                             int(sweep_offset), _ptr(tape), _ptr(trace), _stream()))
+        _lib.check(self.lib.bark_mcmc_sweeps_ex(C.byref(self.dims), _ptr(self.ws), self.dforest.soa(), C.byref(cp),
+                                                int(n_sweeps), C.c_uint64(seed & (2**64 - 1)), int(chain_offset),
+                                                int(sweep_offset), _ptr(tape), _ptr(trace),
+                                                -1 if refresh_every is None else int(refresh_every), _stream()))
 
     def sweeps_timed(self, params: BARKTrainParams, n_sweeps: int, seed: int, chain_offset=0, sweep_offset=0):
         """Measurement variant: returns (ms in the tree-sweep kernel, ms in the hyper kernel), summed over sweeps."""
@@ -121,6 +124,15 @@ class ChainState:
                                                    int(n_sweeps), C.c_uint64(seed & (2**64 - 1)), int(chain_offset),
                                                    int(sweep_offset), C.byref(a), C.byref(b), _stream()))
         return a.value, b.value
+
+    def sweeps_timed3(self, params: BARKTrainParams, n_sweeps: int, seed: int, chain_offset=0, sweep_offset=0):
+        """Measurement variant: (ms tree sweep, ms noise/scale evaluation, ms exact refresh), summed over sweeps."""
+        cp = params.to_c()
+        ms = (C.c_float * 3)()
+        _lib.check(self.lib.bark_mcmc_sweeps_timed3(C.byref(self.dims), _ptr(self.ws), self.dforest.soa(), C.byref(cp),
+                                                    int(n_sweeps), C.c_uint64(seed & (2**64 - 1)), int(chain_offset),
+                                                    int(sweep_offset), ms, _stream()))
+        return float(ms[0]), float(ms[1]), float(ms[2])
 
     def read(self):
         """dict of per-chain device tensors: noise, scale, mll, status, counters (C,8), p_used."""
@@ -154,7 +166,7 @@ class _ColumnOverflow(Exception):
 
 
 def run_bark_sampler(model, data, domain, params: BARKTrainParams, *, seed=None, p_cap=None, tape=None,
-                     return_trace=False, chain_offset=0, device=None, return_info=False):
+                     return_trace=False, chain_offset=0, device=None, return_info=False, refresh_every=None):
     """See `_run_bark_sampler_once`; on leaf-column overflow the run is repeated with twice the capacity
     (deterministic: same seed / tape -> same trajectory)."""
     if seed is None:
@@ -169,7 +181,7 @@ def run_bark_sampler(model, data, domain, params: BARKTrainParams, *, seed=None,
         try:
             return _run_bark_sampler_once(model, data, domain, params, seed=seed, p_cap=cap, tape=tape,
                                           return_trace=return_trace, chain_offset=chain_offset, device=device,
-                                          return_info=return_info)
+                                          return_info=return_info, refresh_every=refresh_every)
         except _ColumnOverflow:
             if cap >= limit:
                 raise _lib.BarkError(f"leaf-column capacity exceeded at p_cap={cap}, the largest this problem size allows")
@@ -177,7 +189,7 @@ def run_bark_sampler(model, data, domain, params: BARKTrainParams, *, seed=None,
 
 
 def _run_bark_sampler_once(model, data, domain, params: BARKTrainParams, *, seed=None, p_cap=None, tape=None,
-                           return_trace=False, chain_offset=0, device=None, return_info=False):
+                           return_trace=False, chain_offset=0, device=None, return_info=False, refresh_every=None):
     """Generate samples from the BARK posterior (src/bark/fitting/bark_sampler.py:95-117).
 
     model  = (forest (C,m,L) NODE_RECORD_DTYPE, noise (C,), scale (C,))
@@ -221,7 +233,8 @@ def _run_bark_sampler_once(model, data, domain, params: BARKTrainParams, *, seed
             return
         tp = tape_d[:, s0:s0 + n_sw].contiguous() if tape_d is not None else None
         tr = torch.zeros((chains, n_sw, m + 1, 3), dtype=torch.float64, device=dev) if return_trace else None
-        st.sweeps(params, n_sw, seed, chain_offset=chain_offset, sweep_offset=s0, tape=tp, trace=tr)
+        st.sweeps(params, n_sw, seed, chain_offset=chain_offset, sweep_offset=s0, tape=tp, trace=tr,
+                  refresh_every=refresh_every)
         if tr is not None:
             traces.append(tr)
 

@@ -157,12 +157,25 @@ int bark_mcmc_sweeps(const bark_mcmc_dims* dims, void* workspace, bark_nodes_soa
                      int64_t n_sweeps, uint64_t seed, int64_t chain_offset, int64_t sweep_offset, const double* tape,
                      double* trace, void* stream);
 
+/* Same, with the refresh policy explicit: the running leaf-space state (B^-1, w, residual, log-det) of a chain is
+ * rebuilt exactly when its noise/scale move is accepted -- where the reference rebuilds K^-1,
+ * bark_sampler.py:276-282 -- and additionally every `refresh_every` sweeps (staggered over the chains; more often
+ * for an ill-conditioned chain).  0: only on accept (the reference's behaviour); -1: the default policy
+ * (8, or 0 when a tape is replayed). */
+int bark_mcmc_sweeps_ex(const bark_mcmc_dims* dims, void* workspace, bark_nodes_soa forest, const bark_params* params,
+                        int64_t n_sweeps, uint64_t seed, int64_t chain_offset, int64_t sweep_offset, const double* tape,
+                        double* trace, int32_t refresh_every, void* stream);
+
 /* Measurement variant (bench only; SYNCHRONISES the stream): same work without tape/trace, with CUDA events
  * recorded on `stream` around every kernel; returns the summed device time of the tree-sweep kernel and of the
  * hyper-step kernel in milliseconds (host pointers). */
 int bark_mcmc_sweeps_timed(const bark_mcmc_dims* dims, void* workspace, bark_nodes_soa forest, const bark_params* params,
                            int64_t n_sweeps, uint64_t seed, int64_t chain_offset, int64_t sweep_offset,
                            float* ms_trees_host, float* ms_hyper_host, void* stream);
+/* ... with the hyper step split: ms3_host[0..2] = tree sweep, noise/scale evaluation, exact refresh. */
+int bark_mcmc_sweeps_timed3(const bark_mcmc_dims* dims, void* workspace, bark_nodes_soa forest, const bark_params* params,
+                            int64_t n_sweeps, uint64_t seed, int64_t chain_offset, int64_t sweep_offset, float* ms3_host,
+                            void* stream);
 
 /* Read-out of per-chain scalars: each (chains) or NULL.  counters (chains, 16) u64:
  * [0 tree proposals issued, 1 valid, 2 accepted, 3 hyper issued, 4 hyper accepted, 5-7 grow/prune/change accepted,

@@ -551,25 +551,41 @@ def test_acquisition_inputs_match_oracle(n, dims, m):
 
 
 def test_cluster_size_does_not_change_the_chain(monkeypatch):
-    """1, 2 or 4 CTAs per chain (BARK_SWEEP_CLUSTER) only change how the leaf-space linear algebra is shared out: the
-    sampled forests are byte-identical and the hyper-parameter samples agree to rounding."""
+    """1 to 16 CTAs per chain (BARK_SWEEP_CLUSTER) only change how the leaf-space linear algebra is shared out: every
+    8-row unit of the DMMA product / update is computed by one warp whatever the cluster size, and the decisions are
+    taken redundantly on identical inputs, so the sampled forests AND hyper-parameters are bit-identical."""
     X, y, bounds, ft, _ = O.synthetic_problem(300, dim=5, cat_dim=1, num_cat=4, m_true=20, seed=12)
     chains, m = 3, 40
     p = B.BARKTrainParams(warmup_steps=25, num_samples=2, steps_per_sample=5, num_chains=chains)
     f0 = np.tile(O.create_empty_forest(m), (chains, 1, 1))
     runs = {}
-    for r in ("1", "2", "4"):
+    for r in ("1", "2", "4", "8", "16"):
         monkeypatch.setenv("BARK_SWEEP_CLUSTER", r)
         runs[r] = B.run_bark_sampler((f0, np.full(chains, 0.1), np.full(chains, 1.0)), (X, y), (bounds, ft), p, seed=77)
     monkeypatch.delenv("BARK_SWEEP_CLUSTER")
-    for r in ("2", "4"):
+    for r in ("2", "4", "8", "16"):
         assert runs[r][0].tobytes() == runs["1"][0].tobytes(), f"forests differ between 1 and {r} CTAs per chain"
         assert np.allclose(runs[r][1], runs["1"][1], rtol=1e-9, atol=0)
 
 
+@pytest.mark.parametrize("kb", ["1", "2", "4"])
+def test_block_size_does_not_change_the_trajectory(monkeypatch, kb):
+    """The speculative block size (8 proposals by default, BARK_SWEEP_KB forces the smaller instantiations that very
+    wide forests fall back to) changes only how much work is batched: same oracle trajectory, byte for byte."""
+    monkeypatch.setenv("BARK_SWEEP_KB", kb)
+    want, trace_o, got, _ = replay_case(n=70, dim=3, cat=1, m=13, chains=2, warm=6, ns=1, sps=4, seed=31)
+    monkeypatch.delenv("BARK_SWEEP_KB")
+    ns_g, noise_g, scale_g, trace_g, info = got
+    fin = np.isfinite(trace_o[..., 0])
+    rel = np.abs(trace_g[..., 1][fin] - trace_o[..., 1][fin]) / np.maximum(np.abs(trace_o[..., 1][fin]), 1e-300)
+    assert rel.max() < 1e-9, rel.max()
+    assert not (trace_o[..., 2] != trace_g[..., 2]).any()
+    assert ns_g.tobytes() == want[0].tobytes()
+
+
 def test_sampler_wide_forest_unpaired_panels():
-    """More than 512 leaf columns in use (m = 320 trees): the matvec / update passes run panel by panel instead of
-    with paired row prefixes; still the oracle's trajectory byte for byte."""
+    """More than 512 leaf columns in use (m = 320 trees, capacity 1280: the block kernel drops to 4 proposals per block
+    to fit shared memory); still the oracle's trajectory byte for byte."""
     want, trace_o, got, _ = replay_case(n=200, dim=4, cat=0, m=320, chains=2, warm=9, ns=1, sps=3, seed=21)
     ns_g, noise_g, scale_g, trace_g, info = got
     leaves = (ns_g["active"] & ns_g["is_leaf"]).sum(axis=(-1, -2))
@@ -617,3 +633,119 @@ def test_tree_agreement_kernel_on_device():
     assert np.array_equal(got.cpu().numpy(), O.forest_gram_matrix(forest, X[:97], X[40:], ft))
     assert np.array_equal(k.forward(x1, x1).cpu().numpy(), O.forest_gram_matrix(forest, X[:97], X[:97], ft))
     assert torch.equal(k.forward(x1, x2, diag=True), torch.ones(97, dtype=torch.float64, device="cuda"))
+
+
+# ------------------------------------------------------------ replay at the BASELINE shapes (configs 2, 3, 4)
+def _burnt_in_start(n, dims, m, chains, burn, seed):
+    """Posterior-sized forests as the common start of a full-scale replay: a short free-running GPU fit."""
+    X, y, bounds, ft, _ = O.synthetic_problem(n, dim=dims[0], cat_dim=dims[1], num_cat=5, m_true=50, seed=seed)
+    f0 = np.tile(O.create_empty_forest(m), (chains, 1, 1))
+    p = B.BARKTrainParams(warmup_steps=burn, num_samples=1, steps_per_sample=1, num_chains=chains)
+    ns, noise, scale = B.run_bark_sampler((f0, np.full(chains, 0.1), np.full(chains, 1.0)), (X, y), (bounds, ft), p,
+                                          seed=seed + 7)
+    return (X, y, bounds, ft), (np.ascontiguousarray(ns[:, -1]), noise[:, -1].copy(), scale[:, -1].copy())
+
+
+@pytest.mark.parametrize("n,dims,m,chains,sweeps,refresh", [
+    (250, (10, 0), 50, 4, 6, None),    # BASELINE config 2 shape
+    (500, (6, 4), 100, 3, 3, None),    # config 3: 6 continuous + 4 categorical (bitmask splits)
+    (2000, (10, 0), 200, 2, 2, None),  # config 4
+    (250, (10, 0), 50, 4, 9, 2),       # the production policy: forced exact refresh (every 2 sweeps -> >= 4 per chain)
+])
+def test_replay_at_baseline_shapes(n, dims, m, chains, sweeps, refresh):
+    """From posterior-sized forests (40 free-running sweeps) the GPU and the oracle replay the same tape: every
+    proposal's log q/prior ratio, proposed log-MLL (1e-9 relative) and accept bit, and the final forests byte for
+    byte -- at the sizes the bench runs, and with the forced refresh of the production path switched on."""
+    (X, y, bounds, ft), start = _burnt_in_start(n, dims, m, chains, 40, seed=n)
+    assert (start[0]["active"] & start[0]["is_leaf"]).sum() > 1.3 * chains * m  # the start is not the empty forest
+    tape = O.make_tape(np.random.default_rng(n + 1), chains, sweeps, m)
+    po = O.BARKTrainParams(warmup_steps=0, num_samples=1, steps_per_sample=sweeps, num_chains=chains)
+    pg = B.BARKTrainParams(warmup_steps=0, num_samples=1, steps_per_sample=sweeps, num_chains=chains)
+    trace_o = np.zeros((chains, sweeps, m + 1, 3))
+    want = O.run_bark_sampler((start[0].copy(), start[1].copy(), start[2].copy()), (X, y), bounds, ft, po, tape=tape,
+                              trace=trace_o)
+    got = B.run_bark_sampler(start, (X, y), (bounds, ft), pg, tape=tape, return_trace=True, refresh_every=refresh)
+    trace_g = got[3]
+    fin = np.isfinite(trace_o[..., 0])
+    assert np.array_equal(fin, np.isfinite(trace_g[..., 0]))
+    tree = fin.copy(); tree[..., -1] = False
+    assert np.allclose(trace_g[..., 0][tree], trace_o[..., 0][tree], rtol=0, atol=1e-12)
+    assert not (trace_o[..., 2] != trace_g[..., 2]).any()
+    # relative to max(|mll|, 1): along these trajectories the log-MLL passes through zero (e.g. -0.196 for one proposed
+    # noise at config 2) while its terms y^T K^-1 y / 2 and log|K| / 2 are O(100); there the oracle's own LU-based value
+    # carries ~1e-10 of absolute rounding, which a purely relative bound would misread as a 1e-9 relative error
+    relf = np.where(fin, np.abs(trace_g[..., 1] - trace_o[..., 1]) / np.maximum(np.abs(trace_o[..., 1]), 1.0), 0.0)
+    worst = np.unravel_index(np.argmax(relf), relf.shape)
+    assert relf.max() < 1e-9, (relf.max(), worst, trace_g[worst], trace_o[worst], np.sort(relf.ravel())[-5:])
+    assert got[0].tobytes() == want[0].tobytes()
+    assert np.allclose(got[1], want[1], rtol=1e-12, atol=0)
+
+
+def test_acceptance_and_heldout_statistics_match_oracle_sampler():
+    """Stochastic parity at BASELINE config 2's size: free-running GPU chains (Philox) and free-running
+    oracle chains (numba RNG) agree, within Monte-Carlo error, on the acceptance rates (all tree moves, change moves,
+    grow/prune moves, noise moves), the share of valid proposals, and the held-out NLPD / MSE
+    (src/bark/utils/metrics.py:20-39) of the posterior-predictive mixture."""
+    n, n_test, m, chains = 250, 200, 50, 10
+    Xa, ya, bounds, ft, _ = O.synthetic_problem(n + n_test, dim=10, cat_dim=0, m_true=50, seed=17)
+    X, y, Xt, yt = np.ascontiguousarray(Xa[:n]), ya[:n].copy(), np.ascontiguousarray(Xa[n:]), ya[n:].reshape(-1)
+    warm, S, sps = 50, 6, 5
+    sweeps = warm + S * sps
+    p = B.BARKTrainParams(warmup_steps=warm, num_samples=S, steps_per_sample=sps, num_chains=chains)
+    f0 = np.tile(O.create_empty_forest(m), (chains, 1, 1))
+    model = (f0, np.full(chains, 0.1), np.full(chains, 1.0))
+    ns_g, no_g, sc_g, tr_g = B.run_bark_sampler(model, (X, y), (bounds, ft), p, seed=4242, return_trace=True)
+    tr_o = np.zeros((chains, sweeps, m + 1, 3))
+    O.seed_numba(4243)
+    ns_o, no_o, sc_o = O.run_bark_sampler((f0.copy(), model[1].copy(), model[2].copy()), (X, y), bounds, ft, p, trace=tr_o)
+
+    def rates(tr):  # per chain, after warm-up
+        t = tr[:, warm:, :-1]
+        valid = np.isfinite(t[..., 0])
+        change = valid & (t[..., 0] == 0.0)      # a valid change move has log q + log prior ratio exactly 0
+        other = valid & ~change                  # grow / prune
+        acc = t[..., 2] > 0
+        f = lambda mask: (acc & mask).sum(axis=(1, 2)) / np.maximum(mask.sum(axis=(1, 2)), 1)
+        return dict(valid=valid.mean(axis=(1, 2)), accept=acc.mean(axis=(1, 2)), accept_change=f(change),
+                    accept_growprune=f(other), accept_noise=(tr[:, warm:, -1, 2] > 0).mean(axis=1))
+
+    rg, ro = rates(tr_g), rates(tr_o)
+    for k in rg:
+        se = np.sqrt(rg[k].var(ddof=1) / chains + ro[k].var(ddof=1) / chains)
+        assert abs(rg[k].mean() - ro[k].mean()) < 4.5 * se + 5e-3, (k, rg[k].mean(), ro[k].mean(), se)
+
+    def heldout(ns, no, sc):  # per-chain NLPD / MSE of the mixture over that chain's samples (GPU predictor for both)
+        out = []
+        for c in range(chains):
+            mu, var = B.forest_predict((ns[c:c + 1], no[c:c + 1], sc[c:c + 1]), (X, y), Xt, (bounds, ft))
+            var = var + no[c].reshape(-1, 1)                       # predict_observed (surrogates/bark.py:85-88)
+            mmu, mvar = B.mixture_of_gaussians_as_normal(mu, var)
+            nl = np.mean(0.5 * np.log(2 * np.pi * mvar) + 0.5 * (yt - mmu) ** 2 / mvar)
+            out.append((nl, np.mean((mmu - yt) ** 2)))
+        return np.array(out)
+
+    hg, ho = heldout(ns_g, no_g, sc_g), heldout(ns_o, no_o, sc_o)
+    for k, name in enumerate(("nlpd", "mse")):
+        se = np.sqrt(hg[:, k].var(ddof=1) / chains + ho[:, k].var(ddof=1) / chains)
+        assert abs(hg[:, k].mean() - ho[:, k].mean()) < 4.5 * se + 1e-3, (name, hg[:, k].mean(), ho[:, k].mean(), se)
+
+
+def test_running_mll_stays_within_1e9_at_low_noise():
+    """Low-noise soak (ill-conditioned B = c I + Z^T Z, cond up to ~1e4): with the adaptive refresh period the
+    running log-MLL carried through hundreds of rank-2 updates stays within 1e-9 (relative) of the log-MLL
+    recomputed from scratch from the same forest by the point-space path (tcgen05 Gram + block LDL^T)."""
+    n, m, chains = 1000, 100, 8
+    X, y, bounds, ft, _ = O.synthetic_problem(n, dim=10, cat_dim=0, m_true=50, seed=23, noise_std=0.01)
+    f0 = np.tile(O.create_empty_forest(m), (chains, 1, 1))
+    st = S.ChainState(f0, np.full(chains, 0.02), np.full(chains, 1.0), X, y, bounds, ft)
+    p = B.BARKTrainParams(num_chains=chains)
+    worst = 0.0
+    for leg in range(6):
+        st.sweeps(p, 50, seed=7, sweep_offset=50 * leg)
+        r = st.read()
+        assert int(r["status"].max()) == 0
+        noise, scale, run = r["noise"].cpu().numpy(), r["scale"].cpu().numpy(), r["mll"].cpu().numpy()
+        scratch = B.forest_mll(st.dforest.to_numpy(), noise, scale, X, y, ft)
+        worst = max(worst, float((np.abs(run - scratch) / np.abs(scratch)).max()))
+    assert noise.min() < 5e-3, noise  # the soak did reach the ill-conditioned regime
+    assert worst < 1e-9, worst
