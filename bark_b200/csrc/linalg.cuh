@@ -520,7 +520,7 @@ __device__ void refine_inverse(double* X, double* Bf, double* R, const int32_t* 
 }
 
 // cond(B) <= (c + n_points) / c for B = c I + Z^T Z: above this bound the Gauss-Jordan inverse is refined
-constexpr double REFINE_COND = 1000.0;
+constexpr double REFINE_COND = 3000.0;
 
 }  // namespace la
 }  // namespace bark

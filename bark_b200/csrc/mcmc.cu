@@ -237,9 +237,10 @@ constexpr int HYPER_REFRESH_EVERY = 8;  // sweeps between forced exact refreshes
 // Forced exact refresh of the running state (B^-1, w, residual, log-det) every `refresh_every` sweeps, staggered over
 // the chains; more often for an ill-conditioned B = c I + Z^T Z (cond <= (c + n) / c), whose rank-2 updates drift
 // faster and whose log-MLL amplifies the drift by 1 / sig: the period shrinks in proportion once the bound passes
-// REFRESH_COND, down to every sweep (measured: running vs from-scratch log-MLL 2e-10 at cond 500 with the period 8,
-// 1.7e-9 at cond 2000 -- tests/test_gpu_parity.py::test_running_mll_stays_within_1e9_at_low_noise).
-constexpr double REFRESH_COND = 500.0;
+// REFRESH_COND, down to every sweep.  Measured with the period 8: running vs from-scratch log-MLL 2e-10 ... 5e-10 at
+// cond ~1700 (BASELINE config 4's posterior noise ~0.006), 1.7e-9 at cond ~5000
+// (tests/test_gpu_parity.py::test_running_mll_stays_within_1e9_at_low_noise).
+constexpr double REFRESH_COND = 2000.0;
 __device__ __forceinline__ bool refresh_due(int refresh_every, double n, double c, int64_t tick) {
     if (refresh_every <= 0) return false;
     const double cond = (n + c) / c;
@@ -382,6 +383,7 @@ hyper_refresh_kernel(WsLayout lay, void* ws) {
             sc->res = sc->yy - q; sc->ldt = ldt;
             sc->mll = mll_from(sc->yy, q, sig2, (double)n, ldt);
             sc->hyper_accept = 0;
+            sc->counters[15] += 1ull;  // exact refreshes of this chain (accepted noise/scale moves + forced ones)
         }
     }
 }

@@ -202,7 +202,7 @@ sweep_block_kernel(WsLayout lay, SbLayout sl, void* ws, bark_nodes_soa forest, b
     for (int e = tid; e < P; e += SB_THREADS) w_s[e] = __ldcg(cv.w + e);
 
     unsigned long long n_valid = 0, n_acc_tot = 0, n_acc_move[3] = {0, 0, 0}, n_valid_move[3] = {0, 0, 0};  // thread 0
-    unsigned long long blk_eval = 0, blk_upd = 0, cols_scanned = 0;
+    unsigned long long blk_eval = 0, blk_upd = 0, blk_upd_rank = 0, cols_scanned = 0;
 
     const uint32_t g_chain = (uint32_t)(chain_offset + chain), g_sweep = (uint32_t)(sweep_offset + sweep_in_call);
     const size_t tape_base =
@@ -743,6 +743,7 @@ sweep_block_kernel(WsLayout lay, SbLayout sl, void* ws, bark_nodes_soa forest, b
             blk_eval += (unsigned long long)E * E;
             cols_scanned += (unsigned long long)E;
             if (na) blk_upd += (unsigned long long)E * E;
+            blk_upd_rank += (unsigned long long)E * E * (unsigned long long)na;
         }
         if (na > 0) {
             // Binv -= sum_s W_s M_s^-1 W_s^T on the lower triangle: C (8x8) += A (8 x 4) B (4 x 8), two accepted
@@ -915,6 +916,7 @@ sweep_block_kernel(WsLayout lay, SbLayout sl, void* ws, bark_nodes_soa forest, b
             sc->counters[11] += blk_eval;      // sum over blocks of extent^2 (one product pass per block)
             sc->counters[12] += blk_upd;       // sum over blocks with an accepted proposal of extent^2 (one update pass)
             sc->counters[13] += cols_scanned;  // leaf-bitset columns scanned for V = Z^T U, per block
+            sc->counters[14] += blk_upd_rank;  // sum over blocks of extent^2 x accepted proposals (rank-2 updates applied)
         }
     }
 }

@@ -42,11 +42,13 @@ class PosteriorState:
         self.slots = forest_slots(forest)
         self.p_max = int(st.read()["p_used"].max().item())
         self.prep = None
+        self.k_pad = None  # one-hot width of the int8 GEMM (multiple of 128): 2 * 7 * k_pad^2 int8 ops per candidate-sample
         # (extents above 768 columns, or tensor_cores=False, use the FP64 gather kernel of csrc/predict.cu)
         nbytes = int(st.lib.bark_predict_prep_bytes(C.byref(st.dims), self.slots, self.p_max)) if (tensor_cores and self.p_max <= 768) else 0
         if nbytes:
             torch = _lib.require_cuda()
             self.prep = torch.empty(nbytes, dtype=torch.uint8, device=st.device)
+            self.k_pad = ((self.p_max + 127) // 128) * 128
             _lib.check(st.lib.bark_predict_prepare(C.byref(st.dims), _ptr(st.ws), st.dforest.soa(), self.slots, self.p_max,
                                                    _ptr(self.prep), _stream()))
 

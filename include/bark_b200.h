@@ -179,8 +179,9 @@ int bark_mcmc_sweeps_timed3(const bark_mcmc_dims* dims, void* workspace, bark_no
 
 /* Read-out of per-chain scalars: each (chains) or NULL.  counters (chains, 16) u64:
  * [0 tree proposals issued, 1 valid, 2 accepted, 3 hyper issued, 4 hyper accepted, 5-7 grow/prune/change accepted,
- *  8-10 grow/prune/change valid, 11 sum of extent^2 over matvec evaluations, 12 same over accepted updates,
- *  13 leaf-bitset columns scanned, 14-15 reserved]. */
+ *  8-10 grow/prune/change valid, 11 sum over proposal blocks of extent^2 (one B^-1 V product pass each), 12 same over
+ *  the blocks that accepted something (one update pass each), 13 leaf-bitset columns scanned (per block),
+ *  14 sum over blocks of extent^2 x accepted proposals, 15 exact refreshes of the running state]. */
 int bark_mcmc_read(const bark_mcmc_dims* dims, const void* workspace, double* noise, double* scale, double* mll,
                    uint32_t* status, uint64_t* counters, int32_t* p_used, void* stream);
 
