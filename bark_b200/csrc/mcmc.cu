@@ -204,7 +204,29 @@ chain_init_kernel(WsLayout lay, void* ws, bark_nodes_soa forest, const double* _
     __syncthreads();
     const double logdet = la::block_sweep<true>(cv.Binv, P, ptot, cv.CK, cv.GK, cv.DG, nullptr, nullptr, s, stp, la::SoloTeam());
     if (((double)n + c) / c > la::REFINE_COND) la::refine_inverse(cv.Binv, cv.Wk, cv.S2, cv.A, c, P, ptot, s, la::SoloTeam());
-    const double q = matvec_w_q(cv.Binv, P, ptot, cv.b, cv.w, s.red);
+    double q = matvec_w_q(cv.Binv, P, ptot, cv.b, cv.w, s.red);
+    for (int pass = 0; pass < 2; ++pass) {  // iterative refinement of w against the exact B = c I + A (see hyper_refresh_kernel)
+        __syncthreads();
+        for (int r = wid; r < ptot; r += nw) {
+            double acc = 0.0;
+            for (int k = lane; k < ptot; k += 32) acc = fma((double)cv.A[(size_t)r * P + k], cv.w[k], acc);
+            acc = warp_sum(acc);
+            if (lane == 0) cv.yv[r] = cv.b[r] - fma(c, cv.w[r], acc);
+        }
+        __syncthreads();
+        for (int r = wid; r < ptot; r += nw) {
+            double acc = 0.0;
+            for (int k = lane; k < ptot; k += 32) acc = fma(cv.Binv[(size_t)r * P + k], cv.yv[k], acc);
+            acc = warp_sum(acc);
+            if (lane == 0) cv.w[r] += acc;
+        }
+        __syncthreads();
+    }
+    {
+        double part = 0.0;
+        for (int k = tid; k < ptot; k += la::THREADS) part = fma(cv.b[k], cv.w[k], part);
+        q = block_sum(part, s.red);
+    }
     const double ldt = logdet - (double)ptot * log(c);
     if (tid == 0) {
         ChainScalars* sc = cv.sc;
@@ -232,14 +254,14 @@ chain_init_kernel(WsLayout lay, void* ws, bark_nodes_soa forest, const double* _
 //                        refreshes K^-1 at the same point, :276-282)
 // =====================================================================================================
 constexpr int HYPER_CLUSTER = 8;
-constexpr int HYPER_REFRESH_EVERY = 8;  // sweeps between forced exact refreshes (0 = only on accept, as the reference)
+constexpr int HYPER_REFRESH_EVERY = 16;  // sweeps between forced exact refreshes (0 = only on accept, as the reference)
 
-// Forced exact refresh of the running state (B^-1, w, residual, log-det) every `refresh_every` sweeps, staggered over
+// Forced exact refresh of B^-1 (and with it w, the residual and log|B|) every `refresh_every` sweeps, staggered over
 // the chains; more often for an ill-conditioned B = c I + Z^T Z (cond <= (c + n) / c), whose rank-2 updates drift
-// faster and whose log-MLL amplifies the drift by 1 / sig: the period shrinks in proportion once the bound passes
-// REFRESH_COND, down to every sweep.  Measured with the period 8: running vs from-scratch log-MLL 2e-10 ... 5e-10 at
-// cond ~1700 (BASELINE config 4's posterior noise ~0.006), 1.7e-9 at cond ~5000
-// (tests/test_gpu_parity.py::test_running_mll_stays_within_1e9_at_low_noise).
+// faster: the period shrinks in proportion once the bound passes REFRESH_COND, down to every sweep.  The sensitive
+// half of the log-MLL, the quadratic form, does not wait for it: hyper_eval_kernel refines w against the exact B every
+// sweep.  Measured at BASELINE config 4 (posterior noise ~0.004, cond ~2500): running vs from-scratch log-MLL
+// 1.7e-10 worst / 1.5e-11 median over 64 chains (scripts/diag_running_vs_scratch.py).
 constexpr double REFRESH_COND = 2000.0;
 __device__ __forceinline__ bool refresh_due(int refresh_every, double n, double c, int64_t tick) {
     if (refresh_every <= 0) return false;
@@ -300,12 +322,53 @@ hyper_eval_kernel(WsLayout lay, void* ws, bark_params prm, int64_t sweep_in_call
     const int ph = s_phi;
     const double sig2 = hp.noise + 1e-6;
     const double c2 = sig2 * (double)m / hp.scale;
-    const double yy = sc->yy, cur_mll = sc->mll;
+    const double yy = sc->yy;
+
+    // ---- once per sweep: iterative refinement of w = B^-1 b against the EXACT B = c I + A (A: integers), then the
+    // residual y^T y - b^T w and the running log-MLL from it.  The quadratic form is the sensitive half of the log-MLL
+    // (amplified by 1 / sig); carried through hundreds of rank-2 updates of an inverse that itself drifts it was off
+    // by up to 8e-9 relative at cond(B) ~2500 (scripts/diag_running_vs_scratch.py), while two P^2 passes with the
+    // drifted inverse as a preconditioner bring it back to ~cond eps.  (log|B| is updated by log|det M| per accepted
+    // proposal, which is benign, and re-anchored by the exact refresh.)
+    {
+        const int lane = tid & 31, wid = tid >> 5, nw = la::THREADS >> 5;
+        const double c_cur = sc->c;
+        for (int r = trank * nw + wid; r < ph; r += tsize * nw) {  // yv = b - B w
+            const int32_t* arow = cv.A + (size_t)r * P;
+            double acc = 0.0;
+            for (int k = lane; k < ph; k += 32) acc = fma((double)__ldcg(arow + k), __ldcg(cv.w + k), acc);
+            acc = warp_sum(acc);
+            if (lane == 0) __stcg(cv.yv + r, cv.b[r] - fma(c_cur, __ldcg(cv.w + r), acc));
+        }
+        team.sync();
+        for (int r = trank * nw + wid; r < ph; r += tsize * nw) {  // w += Binv yv (lower triangle kept by the sweep)
+            double acc = 0.0;
+            for (int k = lane; k < ph; k += 32) {
+                const double e = (k <= r) ? __ldcg(cv.Binv + (size_t)r * P + k) : __ldcg(cv.Binv + (size_t)k * P + r);
+                acc = fma(e, __ldcg(cv.yv + k), acc);
+            }
+            acc = warp_sum(acc);
+            if (lane == 0) __stcg(cv.w + r, __ldcg(cv.w + r) + acc);
+        }
+        team.sync();
+        if (trank == 0) {
+            double part = 0.0;
+            for (int k = tid; k < ph; k += la::THREADS) part = fma(cv.b[k], __ldcg(cv.w + k), part);
+            const double q = block_sum(part, s.red);
+            if (tid == 0) {
+                sc->res = yy - q;
+                sc->mll = mll_from(yy, q, sc->sig, (double)n, sc->ldt);
+            }
+            __syncthreads();
+        }
+    }
+    const double cur_mll = sc->mll;  // (used on rank 0 only)
 
     // B' lower triangle, rows split over the cluster
     for (int r = trank; r < ph; r += tsize)
         for (int k = tid; k <= r; k += la::THREADS)
             __stcg(cv.Wk + (size_t)r * P + k, (double)__ldcg(cv.A + (size_t)r * P + k) + (r == k ? c2 : 0.0));
+    team.sync();  // every CTA is done with yv as the refinement residual
     if (trank == 0)
         for (int k = tid; k < ph; k += la::THREADS) __stcg(cv.yv + k, cv.b[k]);
     team.sync();
@@ -364,7 +427,7 @@ hyper_refresh_kernel(WsLayout lay, void* ws) {
     const double logdet_f = la::block_sweep<true>(cv.Binv, P, ph, cv.CK, cv.GK, cv.DG, nullptr, nullptr, s, &sc->status, team);
     if (((double)n + c2) / c2 > la::REFINE_COND) la::refine_inverse(cv.Binv, cv.Wk, cv.S2, cv.A, c2, P, ph, s, team);
     for (int k = ph + trank * la::THREADS + tid; k < P; k += tsize * la::THREADS) __stcg(cv.Binv + (size_t)k * P + k, 1.0 / c2);
-    // w = Binv b, rows split over the cluster
+    // w = Binv b, rows split over the cluster (hyper_eval_kernel refines w against the exact B once per sweep)
     for (int r = trank * nw + wid; r < ph; r += tsize * nw) {
         const double* row = cv.Binv + (size_t)r * P;
         double acc = 0.0;
