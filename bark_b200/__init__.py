@@ -12,6 +12,6 @@ from .predict import BARKModel, PosteriorState, forest_predict, mixture_of_gauss
 from .sampler import BARKTrainParams, BARKTrainParamsNumba, ChainState, run_bark_sampler  # noqa: F401
 from .acquisition import gp_sample_inverses  # noqa: F401
 from .checkpoint import load_samples, save_samples  # noqa: F401
-from .prior import sample_forest_prior, sample_noise_prior  # noqa: F401
+from .prior import sample_forest_prior, sample_forest_prior_device, sample_noise_prior  # noqa: F401
 from .tree_kernel import TreeAgreementKernel  # noqa: F401
 from .surrogate import BARKPriorSurrogate, BARKSurrogate, Standardize  # noqa: F401

@@ -11,7 +11,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libbark_b200.so")
-SOURCES = ["forest.cu", "gram.cu", "gram_umma.cu", "mll.cu", "mcmc.cu", "predict.cu", "predict_umma.cu", "kinv.cu"]
+SOURCES = ["forest.cu", "gram.cu", "gram_umma.cu", "mll.cu", "mcmc.cu", "predict.cu", "predict_umma.cu", "kinv.cu", "prior.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-shared",

@@ -68,9 +68,14 @@ SIGNATURES = {
                                c_void_p, c_void_p]),
     "bark_mcmc_export": (c_int, [C.POINTER(McmcDims), c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
                                  c_void_p]),
+    "bark_prior_sample": (c_int, [NodesSoA, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_int64, c_double, c_double,
+                                  c_uint64, c_void_p, c_void_p]),
     "bark_predict_scratch_bytes": (c_size_t, [C.POINTER(McmcDims), c_int64]),
     "bark_predict": (c_int, [C.POINTER(McmcDims), c_void_p, NodesSoA, c_void_p, c_int64, c_int, c_double, c_double,
                              c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "bark_predict_cov_scratch_bytes": (c_size_t, [C.POINTER(McmcDims), c_int64]),
+    "bark_predict_cov": (c_int, [C.POINTER(McmcDims), c_void_p, NodesSoA, c_void_p, c_int64, c_void_p, c_void_p, c_void_p,
+                                 c_void_p]),
     "bark_predict_prep_bytes": (c_size_t, [C.POINTER(McmcDims), c_int32, c_int32]),
     "bark_predict_prepare": (c_int, [C.POINTER(McmcDims), c_void_p, NodesSoA, c_int32, c_int32, c_void_p, c_void_p]),
     "bark_predict_umma": (c_int, [C.POINTER(McmcDims), c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_int64, c_void_p,

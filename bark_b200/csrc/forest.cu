@@ -3,6 +3,8 @@
 //   bark_traverse                        : pass_through_forest               (src/bark/forest.py:28-67)
 #include <stdarg.h>
 
+#include <algorithm>
+
 #include "common.cuh"
 #include "forest_device.cuh"
 
@@ -86,15 +88,39 @@ __global__ void __launch_bounds__(CODEC_THREADS) nodes_pack_kernel(bark_nodes_so
 // ------------------------------------------------------------------------------------------------
 constexpr int TRAV_THREADS = 256;   // = points per CTA
 constexpr int TRAV_TREES = 32;      // trees per CTA
+constexpr int TRAV_STAGE = 32;      // node slots staged per tree; a walk that reaches a higher slot reads it from global memory
+
+// Posterior trees use the lowest slots (a grow takes the first two inactive slots, src/bark/fitting/tree_proposals.py:45-58;
+// SURVEY: <= 9 of 100 slots active), so only slots [0, TRAV_STAGE) of every tree are staged: 1/3 of the node bytes of a
+// full 100-slot stage, which otherwise outweigh the leaf ids the CTA writes.  Slots beyond the stage stay reachable.
+__device__ __forceinline__ uint32_t walk_tree_staged(const WalkNode* __restrict__ wn, int staged, const bark_nodes_soa& nodes,
+                                                     int64_t gbase, const double* __restrict__ xp, int xstride,
+                                                     const int* __restrict__ ft, int node_limit) {
+    uint32_t at = 0;
+    for (int it = 0; it < node_limit; ++it) {
+        WalkNode nd;
+        if ((int)at < staged) {
+            nd = wn[at];
+        } else {
+            const int64_t g = gbase + at;
+            nd = make_walk_node(nodes.is_leaf[g], nodes.feature[g], nodes.threshold[g], nodes.left[g], nodes.right[g]);
+        }
+        if (nd.feat_leaf & 0x8000u) return at;
+        const int f = nd.feat_leaf & 0x7fffu;
+        at = goes_left(xp[(size_t)f * xstride], nd.thr, ft[f]) ? nd.left : nd.right;
+    }
+    return at;
+}
 
 __global__ void __launch_bounds__(TRAV_THREADS)
 traverse_kernel(bark_nodes_soa nodes, int64_t m, int node_limit, const double* __restrict__ X, int64_t n_points,
                 int d, const int32_t* __restrict__ feat_types, uint32_t* __restrict__ leaves) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    // layout: WalkNode wn[TRAV_TREES][node_limit] | double xs[d][TRAV_THREADS+1]... (feature-major, padded)
-    //         | uint8 out[TRAV_THREADS][TRAV_TREES+?] | int ft[d]
+    // layout: WalkNode wn[TRAV_TREES][staged] | double xs[d][TRAV_THREADS+1] (feature-major, padded)
+    //         | int ft[d] | uint32 out[TRAV_THREADS][TRAV_TREES+1]
+    const int staged = min(node_limit, TRAV_STAGE);
     WalkNode* wn = reinterpret_cast<WalkNode*>(smem_raw);
-    double* xs = reinterpret_cast<double*>(wn + (size_t)TRAV_TREES * node_limit);
+    double* xs = reinterpret_cast<double*>(wn + (size_t)TRAV_TREES * staged);
     int* ft = reinterpret_cast<int*>(xs + (size_t)d * (TRAV_THREADS + 1));
     uint32_t* outs = reinterpret_cast<uint32_t*>(ft + ((d + 1) & ~1));  // [TRAV_THREADS][TRAV_TREES + 1]
 
@@ -104,10 +130,11 @@ traverse_kernel(bark_nodes_soa nodes, int64_t m, int node_limit, const double* _
     const int64_t p0 = (int64_t)blockIdx.x * TRAV_THREADS;
     const int np = (int)min((int64_t)TRAV_THREADS, n_points - p0);
 
-    // stage trees
+    // stage the low slots of the CTA's trees
     const int64_t node_base = (forest * m + t0) * node_limit;
-    for (int e = threadIdx.x; e < nt * node_limit; e += TRAV_THREADS) {
-        const int64_t g = node_base + e;
+    for (int e = threadIdx.x; e < nt * staged; e += TRAV_THREADS) {
+        const int t = e / staged, sl = e - t * staged;
+        const int64_t g = node_base + (int64_t)t * node_limit + sl;
         wn[e] = make_walk_node(nodes.is_leaf[g], nodes.feature[g], nodes.threshold[g], nodes.left[g], nodes.right[g]);
     }
     for (int e = threadIdx.x; e < d; e += TRAV_THREADS) ft[e] = feat_types[e];
@@ -121,8 +148,9 @@ traverse_kernel(bark_nodes_soa nodes, int64_t m, int node_limit, const double* _
     if ((int)threadIdx.x < np) {
         const double* xp = xs + threadIdx.x;
         for (int t = 0; t < nt; ++t) {
-            outs[threadIdx.x * (TRAV_TREES + 1) + t] =
-                walk_tree(wn + (size_t)t * node_limit, xp, TRAV_THREADS + 1, ft, node_limit);
+            outs[threadIdx.x * (TRAV_TREES + 1) + t] = walk_tree_staged(wn + (size_t)t * staged, staged, nodes,
+                                                                        node_base + (int64_t)t * node_limit, xp,
+                                                                        TRAV_THREADS + 1, ft, node_limit);
         }
     }
     __syncthreads();
@@ -172,7 +200,8 @@ int bark_traverse(bark_nodes_soa nodes, int64_t n_forests, int64_t m, int64_t no
     if (n_forests == 0 || m == 0 || n_points == 0) return BARK_OK;
     BARK_CHECK_ARG(X && feat_types && leaves && nodes.is_leaf, "null pointer");
     BARK_CHECK_ARG(n_forests <= 65535 && ceil_div(m, TRAV_TREES) <= 65535, "grid too large");
-    size_t smem = (size_t)TRAV_TREES * node_limit * sizeof(WalkNode) + (size_t)d * (TRAV_THREADS + 1) * sizeof(double) +
+    size_t smem = (size_t)TRAV_TREES * std::min<int64_t>(node_limit, TRAV_STAGE) * sizeof(WalkNode) +
+                  (size_t)d * (TRAV_THREADS + 1) * sizeof(double) +
                   (size_t)((d + 1) & ~1) * sizeof(int) + (size_t)TRAV_THREADS * (TRAV_TREES + 1) * sizeof(uint32_t);
     BARK_CHECK_ARG(smem <= 220 * 1024, "d * node_limit too large for the shared-memory staging");
     BARK_CUDA(cudaFuncSetAttribute(traverse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -23,7 +23,7 @@ namespace bark {
 constexpr int UT = 128;                 // tile edge (UMMA M = N = 128)
 constexpr int UK = 128;                 // K bytes per tile (one SWIZZLE_128B atom row)
 constexpr int TILE_BYTES = UT * UK;     // 16 KB
-constexpr int U_STAGES = 4;
+constexpr int U_STAGES = 3;             // 96 KB of operand ring: two CTAs per SM, so one tile's epilogue overlaps the other's MMAs
 constexpr int U_THREADS = 128;
 
 __device__ __forceinline__ uint32_t u_smem(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -71,8 +71,15 @@ __device__ __forceinline__ bool u_mbar_try_wait(uint64_t* bar, uint32_t parity) 
         : "memory");
     return ok != 0;
 }
-__device__ __forceinline__ void u_mbar_wait(uint64_t* bar, uint32_t parity) {
+// Bounded wait: a barrier that does not complete within ~2^26 probes (seconds) sets bit 1 of the status word (when the
+// caller passed one) and gives up instead of hanging the GPU; the output of that tile is then invalid.
+__device__ __forceinline__ void u_mbar_wait(uint64_t* bar, uint32_t parity, uint32_t* status = nullptr) {
+    unsigned spins = 0;
     while (!u_mbar_try_wait(bar, parity)) {
+        if (++spins > (1u << 26)) {
+            if (status) atomicOr(status, 2u);
+            break;
+        }
     }
 }
 __device__ __forceinline__ void u_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
@@ -125,9 +132,10 @@ struct GramEpilogue {
     const double* noise;  // per batch or null
     double inv_m, jitter;
     int add_diag;
+    uint32_t* status;     // may be null; bit 1: a pipeline wait timed out
 };
 
-__global__ void __launch_bounds__(U_THREADS, 1)
+__global__ void __launch_bounds__(U_THREADS, 2)
 gram_umma_kernel(const uint8_t* __restrict__ Za, const uint8_t* __restrict__ Zb, int64_t na, int64_t nb, int64_t rt_a,
                  int64_t rt_b, int64_t k_tiles, GramEpilogue ep) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -164,7 +172,7 @@ gram_umma_kernel(const uint8_t* __restrict__ Za, const uint8_t* __restrict__ Zb,
         for (int64_t it = 0; it < KT + U_STAGES - 1; ++it) {
             if (it < KT) {
                 const int s = (int)(it % U_STAGES);
-                if (it >= U_STAGES) u_mbar_wait(empty_bar + s, (uint32_t)((it / U_STAGES - 1) & 1));
+                if (it >= U_STAGES) u_mbar_wait(empty_bar + s, (uint32_t)((it / U_STAGES - 1) & 1), ep.status);
                 u_mbar_expect_tx(full_bar + s, 2 * TILE_BYTES);
                 u_bulk_g2s(tiles + (size_t)s * 2 * TILE_BYTES, a_src + it * TILE_BYTES, TILE_BYTES, full_bar + s);
                 u_bulk_g2s(tiles + (size_t)s * 2 * TILE_BYTES + TILE_BYTES, b_src + it * TILE_BYTES, TILE_BYTES, full_bar + s);
@@ -172,7 +180,7 @@ gram_umma_kernel(const uint8_t* __restrict__ Za, const uint8_t* __restrict__ Zb,
             const int64_t kc = it - (U_STAGES - 1);
             if (kc >= 0) {
                 const int s = (int)(kc % U_STAGES);
-                u_mbar_wait(full_bar + s, (uint32_t)((kc / U_STAGES) & 1));
+                u_mbar_wait(full_bar + s, (uint32_t)((kc / U_STAGES) & 1), ep.status);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t a_addr = u_smem(tiles + (size_t)s * 2 * TILE_BYTES);
                 const uint32_t b_addr = a_addr + TILE_BYTES;
@@ -187,35 +195,49 @@ gram_umma_kernel(const uint8_t* __restrict__ Za, const uint8_t* __restrict__ Zb,
     }
     __syncwarp();
 
-    // ---- epilogue: TMEM -> registers -> global (thread = one accumulator row, 32 columns per load)
-    u_mbar_wait(acc_bar, 0);
+    // ---- epilogue: TMEM -> registers -> shared-memory transpose -> global.  tcgen05.ld hands every thread ONE
+    // accumulator row (32 consecutive columns); stored as such, a warp's store instruction would touch 32 different
+    // rows (32 sectors for 256 bytes).  Each warp therefore turns its 32 x 32 block through a padded shared-memory
+    // tile, so that one store instruction writes 32 consecutive columns of one row (one 256-byte / 128-byte segment).
+    u_mbar_wait(acc_bar, 0, ep.status);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const int64_t row = tr * UT + warp * 32 + lane;
+    // (the operand ring is idle once the accumulator is complete: it doubles as the transpose buffer)
+    double* stage = reinterpret_cast<double*>(tiles) + (size_t)warp * 32 * 33;
+    int32_t* stage_i = reinterpret_cast<int32_t*>(stage);
+    const int64_t row0 = tr * UT + warp * 32;
     const double sc = ep.K ? ep.scale[b] : 0.0;
     const double dg = (ep.K && ep.add_diag) ? __dadd_rn(ep.jitter, ep.noise[b]) : 0.0;
 #pragma unroll 1
     for (int c0 = 0; c0 < UT; c0 += 32) {
         uint32_t v[32];
         tmem_ld_32x32(tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
-        if (row < na) {
-            const int64_t col0 = tc * UT + c0;
-            if (ep.counts) {
-                int32_t* out = ep.counts + (b * na + row) * nb + col0;
+        const int64_t col = tc * UT + c0 + lane;  // this lane's column in the transposed phase
+        if (ep.counts) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j)
-                    if (col0 + j < nb) out[j] = (int32_t)v[j];
+            for (int j = 0; j < 32; ++j) stage_i[lane * 33 + j] = (int32_t)v[j];
+            __syncwarp();
+            if (col < nb) {
+#pragma unroll 4
+                for (int r = 0; r < 32; ++r)
+                    if (row0 + r < na) ep.counts[(b * na + row0 + r) * nb + col] = stage_i[r * 33 + lane];
             }
-            if (ep.K) {
-                double* out = ep.K + (b * na + row) * nb + col0;
+            __syncwarp();
+        }
+        if (ep.K) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    if (col0 + j < nb) {
-                        double x = __dmul_rn(sc, __dmul_rn(ep.inv_m, (double)(int32_t)v[j]));
-                        if (ep.add_diag && col0 + j == row) x = __dadd_rn(x, dg);
-                        out[j] = x;
+            for (int j = 0; j < 32; ++j) stage[lane * 33 + j] = __dmul_rn(sc, __dmul_rn(ep.inv_m, (double)(int32_t)v[j]));
+            __syncwarp();
+            if (col < nb) {
+#pragma unroll 4
+                for (int r = 0; r < 32; ++r) {
+                    if (row0 + r < na) {
+                        double x = stage[r * 33 + lane];
+                        if (ep.add_diag && col == row0 + r) x = __dadd_rn(x, dg);
+                        ep.K[(b * na + row0 + r) * nb + col] = x;
                     }
                 }
             }
+            __syncwarp();
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -268,7 +290,7 @@ int bark_gram_umma(const uint32_t* leaves_a, const uint32_t* leaves_b, int64_t b
     BARK_LAUNCH_CHECK();
     const size_t smem = (size_t)U_STAGES * 2 * TILE_BYTES + 256;
     BARK_CUDA(cudaFuncSetAttribute(gram_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    GramEpilogue ep{counts, K, scale, noise, 1.0 / (double)m, jitter, add_diag};
+    GramEpilogue ep{counts, K, scale, noise, 1.0 / (double)m, jitter, add_diag, status};
     dim3 grid((unsigned)rtb, (unsigned)rta, (unsigned)batch);
     gram_umma_kernel<<<grid, U_THREADS, smem, st>>>(Za, Zb, na, nb, rta, rtb, kt, ep);
     BARK_LAUNCH_CHECK();

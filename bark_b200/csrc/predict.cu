@@ -105,6 +105,72 @@ __global__ void predict_mixture_kernel(WsLayout lay, const void* ws, const doubl
     }
 }
 
+// ---- diag = False (src/bark/tree_kernels/tree_gps.py:107-112): the full n_c x n_c matrix the reference forms,
+//     cov[i][j] = scale - (K_xX K^-1 K_Xx)[i][j] = scale - (scale / m) #{t : leaf_t(x_i) = leaf_t(x_j)} + sig z_i^T B^-1 z_j
+// (the reference subtracts from the SCALAR scale, also off the diagonal; reproduced as written).  Three small kernels:
+// leaf columns + mean per candidate, G = Z_c B^-1 (n_c x P gathers), cov from m gathers of G per pair.
+__global__ void __launch_bounds__(PR_THREADS)
+predict_cols_kernel(WsLayout lay, const void* ws, const WalkNode* __restrict__ table, const double* __restrict__ cand,
+                    int64_t n_c, uint16_t* __restrict__ cols, double* __restrict__ mu) {
+    const int d = (int)lay.d, m = (int)lay.m, L = (int)lay.L;
+    const int64_t sample = blockIdx.y;
+    const int64_t i = (int64_t)blockIdx.x * PR_THREADS + threadIdx.x;
+    if (i >= n_c) return;
+    ChainView cv = chain_view(lay, const_cast<void*>(ws), sample);
+    SharedView sv = shared_view(lay, ws);
+    const WalkNode* tb = table + sample * (int64_t)m * L;
+    const double* xp = cand + i * d;
+    double mean = 0.0;
+    for (int t = 0; t < m; ++t) {
+        const WalkNode* wn = tb + (size_t)t * L;
+        WalkNode nd = wn[0];
+        for (int it = 0; it < L && !(nd.feat_leaf & 0x8000u); ++it) {
+            const int f = nd.feat_leaf & 0x7fffu;
+            nd = wn[goes_left(xp[f], nd.thr, sv.ft[f]) ? nd.left : nd.right];
+        }
+        const int col = __float_as_int(nd.thr);
+        cols[(sample * n_c + i) * m + t] = (uint16_t)col;
+        mean += cv.w[col];
+    }
+    mu[sample * n_c + i] = mean;
+}
+
+__global__ void predict_g_kernel(WsLayout lay, const void* ws, const uint16_t* __restrict__ cols, int64_t n_c,
+                                 double* __restrict__ G) {
+    const int m = (int)lay.m, P = (int)lay.P;
+    const int64_t sample = blockIdx.y, i = blockIdx.x;
+    const double* Binv = chain_view(lay, const_cast<void*>(ws), sample).Binv;
+    const uint16_t* ci = cols + (sample * n_c + i) * m;
+    for (int p = threadIdx.x; p < P; p += blockDim.x) {
+        double acc = 0.0;
+        for (int t = 0; t < m; ++t) {
+            const int c = ci[t];
+            acc += Binv[(size_t)max(c, p) * P + min(c, p)];  // symmetric; the lower triangle is always current
+        }
+        G[(sample * n_c + i) * P + p] = acc;
+    }
+}
+
+__global__ void predict_cov_kernel(WsLayout lay, const void* ws, const uint16_t* __restrict__ cols, const double* __restrict__ G,
+                                   int64_t n_c, double* __restrict__ cov) {
+    const int m = (int)lay.m, P = (int)lay.P;
+    const int64_t sample = blockIdx.y, i = blockIdx.x;
+    const ChainScalars* sc = chain_view(lay, const_cast<void*>(ws), sample).sc;
+    const double scale = sc->scale, sig = sc->sig, s_m = scale / (double)m;
+    const uint16_t* ci = cols + (sample * n_c + i) * m;
+    const double* gi = G + (sample * n_c + i) * P;
+    for (int64_t j = threadIdx.x; j < n_c; j += blockDim.x) {
+        const uint16_t* cj = cols + (sample * n_c + j) * m;
+        double q = 0.0;
+        int same = 0;
+        for (int t = 0; t < m; ++t) {
+            q += gi[cj[t]];
+            same += (ci[t] == cj[t]);
+        }
+        cov[(sample * n_c + i) * n_c + j] = scale - s_m * (double)same + sig * q;
+    }
+}
+
 static size_t table_bytes(const bark_mcmc_dims* dm) {
     return align256((size_t)dm->chains * dm->m * dm->node_limit * sizeof(WalkNode));
 }
@@ -128,6 +194,34 @@ int bark_predict_mixture(const bark_mcmc_dims* dims, const void* workspace, cons
     const WsLayout lay = make_layout(*dims);
     predict_mixture_kernel<<<(unsigned)std::min<int64_t>(ceil_div(n_c, 256), 148 * 8), 256, 0, (cudaStream_t)stream>>>(
         lay, workspace, mu_s, var_s, n_c, y_mean, y_std, add_noise, mu, var);
+    BARK_LAUNCH_CHECK();
+    return BARK_OK;
+}
+
+size_t bark_predict_cov_scratch_bytes(const bark_mcmc_dims* dims, int64_t n_c) {
+    if (!dims || n_c < 0) return 0;
+    return table_bytes(dims) + align256((size_t)dims->chains * (size_t)n_c * dims->m * sizeof(uint16_t)) +
+           align256((size_t)dims->chains * (size_t)n_c * dims->p_cap * sizeof(double));
+}
+
+int bark_predict_cov(const bark_mcmc_dims* dims, const void* workspace, bark_nodes_soa forest, const double* candidates,
+                     int64_t n_c, double* mu, double* cov, void* scratch, void* stream) {
+    BARK_CHECK_ARG(dims && workspace && scratch && forest.is_leaf, "null pointer");
+    BARK_CHECK_ARG(n_c >= 0 && n_c <= 16384, "n_c out of range for the full covariance (0..16384)");
+    if (n_c == 0) return BARK_OK;
+    BARK_CHECK_ARG(candidates && mu && cov, "null pointer");
+    BARK_CHECK_ARG(dims->chains <= 65535, "too many samples per call");
+    const WsLayout lay = make_layout(*dims);
+    cudaStream_t st = (cudaStream_t)stream;
+    WalkNode* table = (WalkNode*)scratch;
+    uint16_t* cols = (uint16_t*)((unsigned char*)scratch + table_bytes(dims));
+    double* G = (double*)((unsigned char*)cols + align256((size_t)dims->chains * (size_t)n_c * dims->m * sizeof(uint16_t)));
+    predict_pack_kernel<<<148 * 2, 256, 0, st>>>(lay, workspace, forest, table);
+    dim3 g1((unsigned)ceil_div(n_c, PR_THREADS), (unsigned)dims->chains);
+    predict_cols_kernel<<<g1, PR_THREADS, 0, st>>>(lay, workspace, table, candidates, n_c, cols, mu);
+    dim3 g2((unsigned)n_c, (unsigned)dims->chains);
+    predict_g_kernel<<<g2, 256, 0, st>>>(lay, workspace, cols, n_c, G);
+    predict_cov_kernel<<<g2, 256, 0, st>>>(lay, workspace, cols, G, n_c, cov);
     BARK_LAUNCH_CHECK();
     return BARK_OK;
 }

@@ -122,8 +122,15 @@ __device__ __forceinline__ bool pu_mbar_try_wait(uint64_t* bar, uint32_t parity)
         : "memory");
     return ok != 0;
 }
-__device__ __forceinline__ void pu_mbar_wait(uint64_t* bar, uint32_t parity) {
+// Bounded wait: gives up after ~2^26 probes and flags BARK_ST_TIMEOUT on the sample's chain state (the host raises)
+// instead of hanging the GPU.
+__device__ __forceinline__ void pu_mbar_wait(uint64_t* bar, uint32_t parity, unsigned* status) {
+    unsigned spins = 0;
     while (!pu_mbar_try_wait(bar, parity)) {
+        if (++spins > (1u << 26)) {
+            atomicOr(status, BARK_ST_TIMEOUT);
+            break;
+        }
     }
 }
 __device__ __forceinline__ void pu_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
@@ -224,6 +231,7 @@ predict_umma_kernel(WsLayout lay, const void* ws, const WalkNode* __restrict__ t
     const int64_t p0 = (int64_t)blockIdx.x * PU_ROWS;
     const int np = (int)min((int64_t)PU_ROWS, n_c - p0);
     ChainView cv = chain_view(lay, const_cast<void*>(ws), sample);
+    unsigned* pu_status = &cv.sc->status;  // bounded pipeline waits flag BARK_ST_TIMEOUT here
     SharedView sv = shared_view(lay, ws);
 
     // ---- setup: barriers, TMEM, staging of the sample's trees / w and of the candidate tile
@@ -311,7 +319,7 @@ predict_umma_kernel(WsLayout lay, const void* ws, const WalkNode* __restrict__ t
                 const int s = ld % nstages;
                 const int nt = ld / (PU_SLICES * kt_n);
                 const uint32_t bytes = (uint32_t)((nt == nt_n - 1) ? last_cols : PU_N) * PU_KB;
-                pu_mbar_wait(empty_bar + s, (uint32_t)((ld / nstages - 1) & 1));
+                pu_mbar_wait(empty_bar + s, (uint32_t)((ld / nstages - 1) & 1), pu_status);
                 pu_mbar_expect_tx(full_bar + s, bytes);
                 pu_bulk_g2s(ring + (size_t)s * PU_B_TILE, src_tiles + (size_t)ld * PU_B_TILE, bytes, full_bar + s);
             }
@@ -325,11 +333,11 @@ predict_umma_kernel(WsLayout lay, const void* ws, const WalkNode* __restrict__ t
                 const int nt = it / PU_SLICES, buf = it & 1, use = it >> 1;
                 const int ncols = (nt == nt_n - 1) ? last_cols : PU_N;
                 const uint32_t idesc = pu_idesc_i8(PU_ROWS, ncols);
-                if (use > 0) pu_mbar_wait(acc_free + buf, (uint32_t)((use - 1) & 1));  // epilogue has drained the buffer
+                if (use > 0) pu_mbar_wait(acc_free + buf, (uint32_t)((use - 1) & 1), pu_status);  // epilogue has drained the buffer
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 for (int kt = 0; kt < kt_n; ++kt, ++ld) {
                     const int s = ld % nstages;
-                    pu_mbar_wait(full_bar + s, (uint32_t)((ld / nstages) & 1));
+                    pu_mbar_wait(full_bar + s, (uint32_t)((ld / nstages) & 1), pu_status);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t a_addr = pu_smem(a_tiles + (size_t)kt * PU_A_TILE);
                     const uint32_t b_addr = pu_smem(ring + (size_t)s * PU_B_TILE);
@@ -359,7 +367,7 @@ predict_umma_kernel(WsLayout lay, const void* ws, const WalkNode* __restrict__ t
 #pragma unroll
             for (int s = 0; s < PU_SLICES; ++s, ++it) {
                 const int buf = it & 1, use = it >> 1;
-                pu_mbar_wait(acc_full + buf, (uint32_t)(use & 1));
+                pu_mbar_wait(acc_full + buf, (uint32_t)(use & 1), pu_status);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 int a = acc[s];
 #pragma unroll

@@ -171,8 +171,11 @@ def gram_umma_device(leaves_a, leaves_b, slots=None, want_counts=True, scale=Non
     ws = torch.empty(max(nbytes, 8), dtype=torch.uint8, device=dev)
     _lib.check(lib.bark_gram_umma(_ptr(leaves_a), _ptr(leaves_b), b, na, nb, m, slots, _ptr(counts), _ptr(K), _ptr(scale),
                                   _ptr(noise), float(jitter), int(noise is not None), _ptr(status), _ptr(ws), _stream()))
-    if int(status.item()) & 1:
+    st = int(status.item())
+    if st & 1:
         raise _lib.BarkError("leaf id >= slots in bark_gram_umma")
+    if st & 2:
+        raise _lib.BarkError("device pipeline wait timed out in bark_gram_umma (internal error)")
     return counts, K
 
 

@@ -55,6 +55,19 @@ class PosteriorState:
     def check(self):
         raise_for_status(self.state.read()["status"].cpu().numpy())
 
+    def predict_cov_device(self, cand_dev):
+        """cand_dev (n_c, d) -> (mu (S, n_c), cov (S, n_c, n_c)): `forest_predict(..., diag=False)`."""
+        torch = _lib.require_cuda()
+        st = self.state
+        n_c = cand_dev.shape[0]
+        mu = torch.empty((self.num_samples, n_c), dtype=torch.float64, device=st.device)
+        cov = torch.empty((self.num_samples, n_c, n_c), dtype=torch.float64, device=st.device)
+        scratch = torch.empty(max(int(st.lib.bark_predict_cov_scratch_bytes(C.byref(st.dims), n_c)), 8), dtype=torch.uint8,
+                              device=st.device)
+        _lib.check(st.lib.bark_predict_cov(C.byref(st.dims), _ptr(st.ws), st.dforest.soa(), _ptr(cand_dev), n_c, _ptr(mu),
+                                           _ptr(cov), _ptr(scratch), _stream()))
+        return mu, cov
+
     def predict_device(self, cand_dev, mode=0, y_mean=0.0, y_std=1.0, add_noise=False):
         """cand_dev (n_c, d) f64 CUDA tensor -> (mu, var) CUDA tensors: (S, n_c) for mode 0, (n_c,) for mode 1."""
         torch = _lib.require_cuda()
@@ -93,11 +106,14 @@ class PosteriorState:
 def forest_predict(model, data, candidates: np.ndarray, domain, diag: bool = True):
     """Per-sample posterior mean and variance at `candidates` (src/bark/tree_kernels/tree_gps.py:80-113).
     Leading sample dims of the model are flattened; returns (mu (S_tot, n_c), var (S_tot, n_c))."""
-    if not diag:
-        raise NotImplementedError("only diag=True is served by the GPU path (the reference's callers use diag=True)")
     _lib.require_cuda()
     _, feat_types = unpack_domain(domain)
     candidates = np.ascontiguousarray(candidates, dtype=np.float64)
+    if not diag:  # the full (S_tot, n_c, n_c) matrix, as the reference forms it (tree_gps.py:107-112)
+        ps = PosteriorState(model, data, feat_types, candidates.shape[1], tensor_cores=False)
+        mu, cov = ps.predict_cov_device(_as_device_f64(candidates, ps.state.device))
+        ps.check()
+        return mu.cpu().numpy(), cov.cpu().numpy()
     ps = PosteriorState(model, data, feat_types, candidates.shape[1])
     mu, var = ps.predict_device(_as_device_f64(candidates, ps.state.device), mode=0)
     ps.check()

@@ -1,6 +1,9 @@
-"""Samples from the BARK prior (src/bark/fitting/bark_prior_sampler.py:15-93).  Like the reference's, this is
-host code (the reference runs it in plain Python, once, outside the fit/predict hot path); the forests it returns
-feed the GPU predictor unchanged.  The structure queries restate `get_node_subspace`
+"""Samples from the BARK prior (src/bark/fitting/bark_prior_sampler.py:15-93).
+
+Two samplers with the same law: `sample_forest_prior` is host code driven by a numpy Generator exactly as the
+reference's (so a reference script that passes its own `rng` keeps its stream semantics), and
+`sample_forest_prior_device` grows all num_samples x m trees in one kernel launch (csrc/prior.cu, Philox streams
+keyed by (seed, sample, tree)) and can leave the forest in HBM for the predictor.  The structure queries restate `get_node_subspace`
 (src/bark/fitting/tree_traversal.py:49-86), `sample_splitting_rule` (src/bark/fitting/tree_proposals.py:78-97) and
 `sample_binary_mask` (src/bark/utils/bit_operations.py:34-58) for a numpy Generator."""
 from __future__ import annotations
@@ -101,3 +104,25 @@ def sample_noise_prior(gamma_shape, gamma_rate, num_samples, rng: np.random.Gene
     """bark_prior_sampler.py:87-93 (a Gamma(shape, rate) draw, as in the reference)."""
     rng = np.random.default_rng() if rng is None else rng
     return rng.gamma(shape=gamma_shape, scale=1 / gamma_rate, size=(num_samples,))
+
+
+def sample_forest_prior_device(m, bounds, feat_types, alpha, beta, num_samples, seed=0, node_limit=100, device=None,
+                               return_device=False):
+    """(num_samples, m, L) forests from the same prior, grown on the GPU (csrc/prior.cu).  Returns the host structured
+    array, or the `DeviceForest` itself with `return_device=True`."""
+    import ctypes as C
+
+    from . import _lib
+    from .forest import DeviceForest, _as_device_f64, _feat_types_device, _ptr, _stream
+    torch = _lib.require_cuda()
+    dev = torch.device(device or "cuda")
+    bounds = np.ascontiguousarray(bounds, dtype=np.float64)
+    df = DeviceForest((num_samples, m, node_limit), dev)
+    status = torch.zeros(1, dtype=torch.int32, device=dev)
+    bd, fd = _as_device_f64(bounds, dev), _feat_types_device(feat_types, dev)
+    _lib.check(_lib.load().bark_prior_sample(df.soa(), int(num_samples), int(m), int(node_limit), _ptr(bd), _ptr(fd),
+                                             int(bounds.shape[0]), float(alpha), float(beta),
+                                             C.c_uint64(int(seed) & (2**64 - 1)), _ptr(status), _stream()))
+    if int(status.item()) & _lib.ST_TREE_OVERFLOW:
+        raise OverflowError("The tree container is not large enough")  # tree_proposals.py:57-58
+    return df if return_device else df.to_numpy()

@@ -128,21 +128,28 @@ class BARKPriorSurrogate(BARKSurrogate):
     `fit` only stores the training data and draws `num_samples` prior forests / noise values; `predict` is the
     same GPU path as for posterior samples."""
 
-    def __init__(self, domain, *, num_samples=5, sample_seed=0, gamma_prior_shape=2.5, gamma_prior_rate=9.0, **kwargs):
+    def __init__(self, domain, *, num_samples=5, sample_seed=0, gamma_prior_shape=2.5, gamma_prior_rate=9.0,
+                 prior_on_device=False, **kwargs):
         # defaults of the reference data model (src/bofire_mixed/data_models/surrogates/bark.py:74-86):
         # inverse-gamma(2.5, 9.0) noise prior and a fixed sample_seed=0, not the posterior surrogate's 1.5 / 5.0
         super().__init__(domain, num_samples=num_samples, gamma_prior_shape=gamma_prior_shape,
                          gamma_prior_rate=gamma_prior_rate, **kwargs)
         self.sample_seed = sample_seed
         self.sample_rng = np.random.default_rng(sample_seed)
+        self.prior_on_device = bool(prior_on_device)  # grow the forests with csrc/prior.cu instead of the host loop
 
     def fit(self, X: np.ndarray, Y: np.ndarray):
         from .prior import sample_forest_prior, sample_noise_prior
         Y = np.asarray(Y, dtype=np.float64).reshape(-1, 1)
         self.train_data = (np.ascontiguousarray(X, dtype=np.float64), self.scaler(Y, train=True))
         bounds, feat_types = unpack_domain(self.domain)
-        self.forest = sample_forest_prior(self.num_trees, bounds, feat_types, self.alpha, self.beta, self.num_samples,
-                                          self.sample_rng)
+        if self.prior_on_device:
+            from .prior import sample_forest_prior_device
+            self.forest = sample_forest_prior_device(self.num_trees, bounds, feat_types, self.alpha, self.beta,
+                                                     self.num_samples, seed=int(self.sample_rng.integers(2**63)))
+        else:
+            self.forest = sample_forest_prior(self.num_trees, bounds, feat_types, self.alpha, self.beta, self.num_samples,
+                                              self.sample_rng)
         self.noise = sample_noise_prior(self.gamma_prior_shape, self.gamma_prior_rate, self.num_samples, self.sample_rng)
         self.scale = np.ones((self.num_samples,))
         self._posterior = None

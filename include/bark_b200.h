@@ -214,6 +214,12 @@ int bark_predict(const bark_mcmc_dims* dims, const void* workspace, bark_nodes_s
                  int64_t n_c, int mode, double y_mean, double y_std, int add_noise, double* mu, double* var,
                  void* scratch, void* stream);
 
+/* diag = False of forest_predict (src/bark/tree_kernels/tree_gps.py:107-112): per-sample mean mu (samples, n_c) and the
+ * FULL matrix cov (samples, n_c, n_c) = scale - K_xX K^-1 K_Xx as the reference forms it (n_c <= 16384). */
+size_t bark_predict_cov_scratch_bytes(const bark_mcmc_dims* dims, int64_t n_c);
+int bark_predict_cov(const bark_mcmc_dims* dims, const void* workspace, bark_nodes_soa forest, const double* candidates,
+                     int64_t n_c, double* mu, double* cov, void* scratch, void* stream);
+
 /* Tensor-core predict (leaf-column extent p_max <= 768): per posterior sample, B^-1 is sliced once into 7 int8 digit
  * planes of a 54-bit fixed-point representation (bark_predict_prepare, into `prep`), then for every tile of 128
  * candidates z^T B^-1 z is an exact int8 one-hot GEMM on tcgen05 with masked int32 row sums (bark_predict_umma:
@@ -226,6 +232,14 @@ int bark_predict_umma(const bark_mcmc_dims* dims, const void* workspace, const v
                       const double* candidates, int64_t n_c, double* mu, double* var, void* stream);
 int bark_predict_mixture(const bark_mcmc_dims* dims, const void* workspace, const double* mu_s, const double* var_s,
                          int64_t n_c, double y_mean, double y_std, int add_noise, double* mu, double* var, void* stream);
+
+/* ---- 8f-2: forests drawn from the BARK tree prior on the device (_sample_single_forest,
+ * src/bark/fitting/bark_prior_sampler.py:15-62): every tree of `forest` (n_samples * m trees of node_limit slots, SoA) is
+ * reset to a root leaf and grown by the depth prior alpha (1 + depth)^-beta with split rules drawn like a grow proposal's.
+ * Philox streams keyed by (seed, sample, tree); *status |= BARK_ST_TREE_OVERFLOW if a tree runs out of slots. */
+int bark_prior_sample(bark_nodes_soa forest, int64_t n_samples, int64_t m, int64_t node_limit, const double* bounds,
+                      const int32_t* feat_types, int64_t d, double alpha, double beta, uint64_t seed, uint32_t* status,
+                      void* stream);
 
 #ifdef __cplusplus
 }

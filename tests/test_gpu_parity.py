@@ -749,3 +749,83 @@ def test_running_mll_stays_within_1e9_at_low_noise():
         worst = max(worst, float((np.abs(run - scratch) / np.abs(scratch)).max()))
     assert noise.min() < 5e-3, noise  # the soak did reach the ill-conditioned regime
     assert worst < 1e-9, worst
+
+
+# ------------------------------------------------------------ SURVEY 8f-2 remainder, diag=False
+def test_forest_predict_full_covariance_matches_oracle():
+    """`forest_predict(..., diag=False)` (src/bark/tree_kernels/tree_gps.py:107-112): the full (S, n_c, n_c) matrix
+    scale - K_xX K^-1 K_Xx as the reference forms it; its diagonal is the diag=True variance."""
+    X, y, bounds, ft, _ = O.synthetic_problem(80, dim=3, cat_dim=1, num_cat=4, m_true=10, seed=9)
+    chains, m = 2, 14
+    p = B.BARKTrainParams(warmup_steps=15, num_samples=2, steps_per_sample=3, num_chains=chains)
+    f0 = np.tile(O.create_empty_forest(m), (chains, 1, 1))
+    model = B.run_bark_sampler((f0, np.full(chains, 0.1), np.full(chains, 1.0)), (X, y), (bounds, ft), p, seed=3)
+    cand = np.ascontiguousarray(np.vstack([X[:5], O.synthetic_problem(32, dim=3, cat_dim=1, num_cat=4, m_true=10, seed=10)[0]]))
+    mu, cov = B.forest_predict(model, (X, y), cand, (bounds, ft), diag=False)
+    mu_o, cov_o = O.forest_predict(model, (X, y), cand, ft, diag=False)
+    assert cov.shape == (chains * 2, 37, 37)
+    assert np.allclose(mu, mu_o, rtol=1e-9, atol=1e-11)
+    assert np.allclose(cov, cov_o, rtol=1e-8, atol=1e-10)
+    _, var = B.forest_predict(model, (X, y), cand, (bounds, ft), diag=True)
+    assert np.allclose(np.diagonal(cov, axis1=1, axis2=2), var, rtol=1e-9, atol=1e-11)
+
+
+def test_device_prior_sampler_law_and_structure():
+    """csrc/prior.cu grows forests from the same prior as the host sampler (bark_prior_sampler.py:15-62): valid tree
+    structure, rules inside the node's feasible box, and the same depth / leaf-count law as the host sampler within
+    Monte-Carlo error; reproducible by seed."""
+    from bark_b200 import prior
+    bounds = np.array([[0.0, 1.0], [-2.0, 3.0], [0.0, 31.0], [2.0, 9.0]])
+    ft = np.array([2, 2, 0, 1])
+    m, S = 200, 12
+    dev = B.sample_forest_prior_device(m, bounds, ft, 0.95, 2.0, S, seed=5)
+    assert dev.shape == (S, m, 100) and dev.dtype == B.NODE_RECORD_DTYPE
+    assert dev.tobytes() == B.sample_forest_prior_device(m, bounds, ft, 0.95, 2.0, S, seed=5).tobytes()
+    assert dev.tobytes() != B.sample_forest_prior_device(m, bounds, ft, 0.95, 2.0, S, seed=6).tobytes()
+    for tree in dev.reshape(-1, 100)[:400]:
+        assert tree[0]["active"] and tree[0]["depth"] == 0
+        for i in np.flatnonzero(tree["active"]):
+            nd = tree[i]
+            sub = prior.get_node_subspace(tree, int(i), bounds, ft)
+            if not nd["is_leaf"]:
+                l, r, f = int(nd["left"]), int(nd["right"]), int(nd["feature_idx"])
+                assert tree[l]["active"] and tree[r]["active"] and tree[l]["parent"] == i and tree[r]["parent"] == i
+                assert tree[l]["depth"] == nd["depth"] + 1 == tree[r]["depth"]
+                if ft[f] == 0:
+                    assert 0 < int(nd["threshold"]) < int(sub[f, 1]) and int(nd["threshold"]) & ~int(sub[f, 1]) == 0
+                elif ft[f] == 1:
+                    assert sub[f, 0] <= nd["threshold"] < sub[f, 1]
+                else:
+                    assert np.float32(sub[f, 0]) <= nd["threshold"] <= np.float32(sub[f, 1])
+    host = B.sample_forest_prior(m, bounds, ft, 0.95, 2.0, S, np.random.default_rng(8))
+
+    def stats(fr):  # per sample forest: mean leaves per tree, mean max depth, share of split roots
+        leaves = (fr["active"] & fr["is_leaf"]).sum(axis=-1)
+        depth = np.where(fr["active"] & fr["is_leaf"], fr["depth"], 0).max(axis=-1)
+        return leaves.mean(axis=1), depth.mean(axis=1), (fr[:, :, 0]["is_leaf"] == 0).mean(axis=1)
+
+    for a, b, name in zip(stats(dev), stats(host), ("leaves/tree", "max depth", "root split")):
+        se = np.sqrt(a.var(ddof=1) / S + b.var(ddof=1) / S)
+        assert abs(a.mean() - b.mean()) < 4.5 * se + 1e-3, (name, a.mean(), b.mean(), se)
+    sur = B.BARKPriorSurrogate((bounds, ft), num_samples=3, num_trees=10, prior_on_device=True)
+    X = np.column_stack([np.random.default_rng(0).random((20, 2)), np.random.default_rng(1).integers(0, 5, 20),
+                         np.random.default_rng(2).integers(2, 9, 20)]).astype(np.float64)
+    mu, sd = sur.fit(X, np.arange(20.0)).predict(X[:4])
+    assert mu.shape == (4, 1) and np.all(np.isfinite(mu)) and np.all(sd > 0)
+
+
+def test_reference_regression_example_on_swapped_imports():
+    """scripts/example_regression.py = examples/regression/regression.py:75-119 with the imports swapped: BoFire-style data
+    model -> surrogate_map -> fit(experiments DataFrame) -> predict(DataFrame) -> NLPD / MSE.  The fitted surrogate must
+    beat the trivial predictor (the training mean) on held-out TreeFunction data with mixed inputs."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("example_regression",
+                                                  os.path.join(os.path.dirname(os.path.dirname(__file__)), "scripts",
+                                                               "example_regression.py"))
+    ex = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ex)
+    df = ex.main(0, 150, 80, 1, dict(num_chains=4, num_trees=30, warmup_steps=60, num_samples=4, steps_per_sample=5))
+    assert list(df.columns) == ["NLPD", "MSE", "Time"] and np.all(np.isfinite(df.to_numpy()))
+    bench = ex.TreeFunctionBenchmark()
+    y = bench.f(bench.sample(2000, 1), seed=1)["y"].to_numpy()
+    assert df["MSE"].iloc[0] < 0.6 * y.var(), (df, y.var())

@@ -211,3 +211,31 @@ def test_distributed_sampler_rejects_more_ranks_than_chains_on_every_rank(monkey
         with pytest.raises(ValueError, match="more ranks"):
             D.run_bark_sampler_distributed((np.tile(f, (2, 1, 1)), np.ones(2), np.ones(2)), (None, None), None,
                                            sampler.BARKTrainParams(num_chains=2), seed=1)
+
+
+def test_bofire_compat_transform_and_validation():
+    """The pandas / BoFire-shaped adapter: ORDINAL encoding of label-valued categoricals in feature order, the data
+    model's validator (src/bofire_mixed/data_models/surrogates/bark.py:42-61), defaults of both data models."""
+    import pandas as pd
+    from bark_b200 import bofire_compat as BC
+    from bark_b200.domain import CategoricalInput, ContinuousInput, DiscreteInput, Inputs
+    inputs = Inputs([ContinuousInput("a", (0, 1)), CategoricalInput("c", ["u", "v", "w"]), DiscreteInput("k", [1, 2, 5])])
+    df = pd.DataFrame({"k": [5, 1], "c": ["w", "u"], "a": [0.25, 0.5], "y": [1.0, 2.0]})
+    X = BC.transform_inputs(inputs, df)
+    assert X.dtype == np.float64 and np.array_equal(X, [[0.25, 2.0, 5.0], [0.5, 0.0, 1.0]])
+    with pytest.raises(ValueError):
+        BC.transform_inputs(inputs, pd.DataFrame({"a": [0.1], "c": ["zz"], "k": [1]}))
+    dm = BC.BARKSurrogate(inputs=inputs, outputs=BC.Outputs())
+    assert dm.input_preprocessing_specs == {"c": "ORDINAL"}
+    assert (dm.warmup_steps, dm.num_samples, dm.steps_per_sample, dm.num_trees, dm.num_chains) == (50, 5, 10, 50, 1)
+    assert (dm.gamma_prior_shape, dm.gamma_prior_rate, dm.grow_prune_weight, dm.change_weight) == (1.5, 5.0, 0.5, 1.0)
+    with pytest.raises(ValueError, match="ordinal"):
+        BC.BARKSurrogate(inputs=inputs, outputs=BC.Outputs(), input_preprocessing_specs={"c": "ONE_HOT"})
+    pm = BC.BARKPriorSurrogate(inputs=inputs, outputs=BC.Outputs())
+    assert (pm.gamma_prior_shape, pm.gamma_prior_rate, pm.sample_seed) == (2.5, 9.0, 0)
+    sur = BC.surrogate_map(dm)
+    assert sur.is_fitted is False and sur.bark_params.num_chains == 1
+    w = sur.bark_params.proposal_weights
+    assert np.allclose(w, [0.25, 0.25, 0.5])  # _bark_params_to_jitclass, surrogates/bark.py:24-36
+    prior = BC.surrogate_map(pm).fit(df)  # drawing from the prior is host code; no GPU needed
+    assert prior.forest.shape == (5, 50, 100) and prior.train_data[0].shape == (2, 3)
