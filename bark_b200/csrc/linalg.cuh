@@ -198,32 +198,19 @@ __device__ __forceinline__ void load_pivot_block(const double* G, int64_t ld, in
 // Schur complements; their product is det D).  Returns false (uniformly) if a pivot is not positive.
 // Register-resident: every thread owns 8 fixed entries (rows r0 + 8 i, column c) of the 64 x 64 block and only
 // the next pivot row / column travel through shared memory (double-buffered), one barrier per pivot.
-// 1 / x to within an ulp or two: single-precision seed + two Newton steps (four dependent DFMAs instead of the
-// ~40-instruction IEEE division sequence; the pivot reciprocal sits on the serial path of every sweep step).
-__device__ __forceinline__ double fast_rcp(double x) {
-    double r = (double)__frcp_rn((float)x);
-    r = fma(r, fma(-x, r, 1.0), r);
-    r = fma(r, fma(-x, r, 1.0), r);
-    return r;
-}
-
 __device__ __forceinline__ bool sweep_pivot_block(Smem& s) {
     const int tid = threadIdx.x;
     const int c = tid & (NB - 1), r0 = tid >> 6;  // THREADS / NB = 8 row phases
     double v[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] = s.D[r0 + 8 * i][c];
-    // pivot row / column buffers: [2][NB] each, carved from s.As (free while the pivot block is processed); the
-    // reciprocal of the next pivot travels with them, computed ONCE by the thread that owns the pivot entry (every
-    // thread dividing for itself made the step issue-bound: 16 warps x ~40 instructions)
+    // pivot row / column buffers: [2][NB] each, carved from s.As (free while the pivot block is processed)
     double* colb = &s.As[0][0];
     double* rowb = colb + 2 * NB;
-    double* ipb = rowb + 2 * NB;  // [2]
     if (tid < NB) {
         colb[tid] = s.D[tid][0];
         rowb[tid] = s.D[0][tid];
     }
-    if (tid == 0) ipb[0] = fast_rcp(s.D[0][0]);
     __syncthreads();
     bool ok = true;
     for (int j = 0; j < NB; ++j) {
@@ -237,9 +224,9 @@ __device__ __forceinline__ bool sweep_pivot_block(Smem& s) {
         for (int i = 0; i < 8; ++i) cr[i] = colv[r0 + 8 * i];
         const double p = colv[j];
         const double rowc = rowv[c];
-        const double ip = ipb[j & 1];
         if (tid == 0) s.piv[j] = p;
         if (!(p > 0.0)) ok = false;
+        const double ip = 1.0 / p;
         const double rc = rowc * ip;
         const bool cj = (c == j);
 #pragma unroll
@@ -251,10 +238,7 @@ __device__ __forceinline__ bool sweep_pivot_block(Smem& s) {
             if (r == j) x = cj ? -ip : rc;            // pivot row
             v[i] = x;
             if (c == j + 1) coln[r] = x;
-            if (r == j + 1) {
-                rown[c] = x;
-                if (c == j + 1) ipb[(j + 1) & 1] = fast_rcp(x);  // the next pivot
-            }
+            if (r == j + 1) rown[c] = x;
         }
         __syncthreads();
     }
