@@ -36,7 +36,7 @@ def main(paths):
         hdr, units = rows[0], rows[1]
         col = {h: i for i, h in enumerate(hdr)}
         for r in rows[2:]:
-            name = re.sub(r"\(.*", "", r[col["Kernel Name"]]).replace("bark::", "").strip()
+            name = re.sub(r"\(.*", "", r[col["Kernel Name"]]).replace("bark::", "").replace("void ", "").strip()
             name = re.sub(r"<.*", "", name)
             out = {"kernel": name}
             for k in KEEP:
