@@ -308,6 +308,8 @@ sweep_block_kernel(WsLayout lay, SbLayout sl, void* ws, bark_nodes_soa forest, b
             const double* xf = sv.Xt + (size_t)pf * npad;
             double eta_p = 0.0;
             int cnt_p = 0;
+            const bool numeric = ftype != FEAT_CAT;
+            const double thr_d = (double)pthr;
             for (int ch = 0; ch * 32 < wd; ++ch) {
                 const int wl = ch * 32 + lane;
                 uint32_t wb_l = 0u, wa_l = 0u;
@@ -315,46 +317,54 @@ sweep_block_kernel(WsLayout lay, SbLayout sl, void* ws, bark_nodes_soa forest, b
                     wb_l = __ldcg(cv.bits + (size_t)pb * wd + wl);
                     if (mv == MOVE_CHANGE) wa_l = __ldcg(cv.bits + (size_t)pa * wd + wl);
                 }
+                if (!live || mv == MOVE_PRUNE) {
+                    // prune: u is the whole right leaf, so the mask IS its bitset (and eta its entry of b = Z^T y, below);
+                    // a dead slot gets empty masks.  One coalesced pass, no point data needed.
+                    if (wl < wd && (wl % nparts) == part) {
+                        upos[j * wd + wl] = wb_l;
+                        uneg[j * wd + wl] = 0u;
+                        cnt_p += __popc(wb_l);
+                    }
+                    continue;
+                }
                 for (int ww0 = part; ww0 < 32; ww0 += 8 * nparts) {
                     double xv[8], yv[8];
 #pragma unroll
                     for (int u = 0; u < 8; ++u) {
                         const int ww = ww0 + u * nparts, i = (ch * 32 + ww) * 32 + lane;
                         xv[u] = yv[u] = 0.0;
-                        if (live && ww < 32 && i < n) {
+                        if (ww < 32 && i < n) {
                             yv[u] = sv.y[i];
-                            if (mv != MOVE_PRUNE) xv[u] = xf[i];
+                            xv[u] = xf[i];
                         }
                     }
 #pragma unroll
                     for (int u = 0; u < 8; ++u) {
                         const int ww = ww0 + u * nparts, w = ch * 32 + ww, i = w * 32 + lane;
                         if (ww >= 32 || w >= wd) break;  // warp-uniform
-                        const uint32_t wbw = __shfl_sync(0xffffffffu, wb_l, ww), waw = __shfl_sync(0xffffffffu, wa_l, ww);
-                        bool pos = false, neg = false;
-                        if (live && i < n) {
-                            const bool in_b = (wbw >> lane) & 1u;
-                            if (mv == MOVE_GROW) {
-                                if (in_b) pos = !goes_left(xv[u], pthr, ftype);
-                            } else if (mv == MOVE_PRUNE) {
-                                pos = in_b;
-                            } else {  // change: b = left child's column, a = right child's column
-                                const bool in_a = (waw >> lane) & 1u;
-                                if (in_a || in_b) {
-                                    const bool gl = goes_left(xv[u], pthr, ftype);
-                                    pos = in_b && !gl;
-                                    neg = in_a && gl;
-                                }
-                            }
+                        const uint32_t wbw = __shfl_sync(0xffffffffu, wb_l, ww);
+                        const bool gl = numeric ? (xv[u] <= thr_d) : goes_left(xv[u], pthr, ftype);
+                        const bool in_b = ((wbw >> lane) & 1u) && i < n;
+                        const bool pos = in_b && !gl;  // grow: the leaf's points that go right; change: left child's that go right
+                        bool neg = false;
+                        if (mv == MOVE_CHANGE) {       // ... and the right child's (column a) that now go left
+                            const uint32_t waw = __shfl_sync(0xffffffffu, wa_l, ww);
+                            neg = ((waw >> lane) & 1u) && gl && i < n;
                         }
                         const unsigned bp = __ballot_sync(0xffffffffu, pos), bn = __ballot_sync(0xffffffffu, neg);
                         if (lane == 0) { upos[j * wd + w] = bp; uneg[j * wd + w] = bn; }
-                        if (pos) eta_p += yv[u];
-                        if (neg) eta_p -= yv[u];
+                        eta_p += pos ? yv[u] : 0.0;
+                        eta_p -= neg ? yv[u] : 0.0;
                         cnt_p += __popc(bp) + __popc(bn);
                     }
                 }
             }
+            if (live && mv == MOVE_PRUNE) {
+                // eta = sum of y over the right leaf = its entry of b; counted once per slot (its part-0 warp), and the
+                // per-lane popcounts above are per-lane partial counts: fold them over the warp
+                eta_p = (part == 0 && lane == 0) ? __ldcg(cv.b + pb) : 0.0;
+            }
+            if (!live || mv == MOVE_PRUNE) cnt_p = warp_sum_int(cnt_p);  // (the ballot path counts warp-wide already)
             // per-slot totals: eta (fixed tree over lanes, fixed order over the slot's warps), n_u (exact integers)
             const double e = warp_sum(eta_p);
             if (lane == 0) { red[wid] = e; red[SB_WARPS + wid] = (double)cnt_p; }
@@ -415,15 +425,20 @@ sweep_block_kernel(WsLayout lay, SbLayout sl, void* ws, bark_nodes_soa forest, b
 #pragma unroll
                 for (int j = 0; j < KS; ++j) cnt[j] += __shfl_xor_sync(0xffffffffu, cnt[j], 1);
                 if (q < r1) {
+                    // a prune's column of A: all loads before the first (distributed) shared-memory store
+                    const unsigned prmask = valmask & ~scanmask;
+                    if (prmask) {
+#pragma unroll
+                        for (int j = 0; j < KS; ++j)
+                            if (((prmask >> j) & 1u) && ((j & 1) == part || KS == 1))
+                                cnt[j] = (q < p_hi) ? __ldcg(cv.A + (size_t)q * P + ctl->prop[j].b) : 0;
+                    }
                     // the two threads of a column write its KS values to every CTA of the cluster
 #pragma unroll
                     for (int j = 0; j < KS; ++j) {
-                        if ((j & 1) == part || KS == 1) {
-                            double val = (double)cnt[j];
-                            if (((valmask & ~scanmask) >> j) & 1u)
-                                val = (q < p_hi) ? (double)__ldcg(cv.A + (size_t)q * P + ctl->prop[j].b) : 0.0;
-                            if (KS > 1 || part == 0)
-                                for (int r = 0; r < R; ++r) cluster.map_shared_rank(V, r)[(size_t)j * PS + q] = val;
+                        if (((j & 1) == part || KS == 1) && (KS > 1 || part == 0)) {
+                            const double val = (double)cnt[j];
+                            for (int r = 0; r < R; ++r) cluster.map_shared_rank(V, r)[(size_t)j * PS + q] = val;
                         }
                     }
                 }
@@ -747,9 +762,8 @@ sweep_block_kernel(WsLayout lay, SbLayout sl, void* ws, bark_nodes_soa forest, b
         }
         if (na > 0) {
             // Binv -= sum_s W_s M_s^-1 W_s^T on the lower triangle: C (8x8) += A (8 x 4) B (4 x 8), two accepted
-            // proposals per DMMA step (k index = 2 * (accepted s mod 2) + component).  Row blocks are paired
-            // (I, nb8-1-I) so that every unit costs nb8 + 1 blocks; eight blocks' loads in flight, then their stores
-            // (a load -> store loop on the same array is serialised by possible aliasing).
+            // proposals per DMMA step (k index = 2 * (accepted s mod 2) + component); eight tiles' loads in flight, then
+            // their stores (a load -> store loop on the same array is serialised by possible aliasing).
             constexpr int MAXST = (KS + 1) / 2;
             const int nsteps = (na + 1) >> 1;
             const int s_of = lk >> 1, comp = lk & 1;
@@ -770,34 +784,88 @@ sweep_block_kernel(WsLayout lay, SbLayout sl, void* ws, bark_nodes_soa forest, b
                 }
             }
             for (int s = 0; s < na; ++s) n_prune += (ctl->acc[s].move == MOVE_PRUNE);
-            for (int pu = gw; pu < (nb8 + 1) / 2; pu += ngw) {
-                for (int half = 0; half < 2; ++half) {
-                    const int I = half ? nb8 - 1 - pu : pu;
-                    if (half && I == pu) break;
-                    const int row = 8 * I + lq;
-                    double afr[MAXST];
-#pragma unroll
-                    for (int st = 0; st < MAXST; ++st) {
-                        afr[st] = 0.0;
-                        if (2 * st + s_of < na) afr[st] = -(comp ? Wv[woff[st] + row] : Wd[woff[st] + row]);
+            if (ngw <= 2 * SB_WARPS) {
+                // up to two CTAs per chain: row blocks paired (I, nb8-1-I), every unit nb8 + 1 tiles, about one unit per warp
+                // (the leanest inner loop: the A fragment and the row pointer are per unit, not per tile)
+                for (int pu = gw; pu < (nb8 + 1) / 2; pu += ngw) {
+                    for (int half = 0; half < 2; ++half) {
+                        const int I = half ? nb8 - 1 - pu : pu;
+                        if (half && I == pu) break;
+                        const int row = 8 * I + lq;
+                        double afr[MAXST];
+    #pragma unroll
+                        for (int st = 0; st < MAXST; ++st) {
+                            afr[st] = 0.0;
+                            if (2 * st + s_of < na) afr[st] = -(comp ? Wv[woff[st] + row] : Wd[woff[st] + row]);
+                        }
+                        double* rowp = cv.Binv + (size_t)row * P + 2 * lk;
+                        for (int J0 = 0; J0 <= I; J0 += 8) {
+                            double2 cc[8];
+    #pragma unroll
+                            for (int u = 0; u < 8; ++u) cc[u] = (J0 + u <= I) ? sb_ldcg2(rowp + 8 * (J0 + u)) : make_double2(0.0, 0.0);
+    #pragma unroll
+                            for (int u = 0; u < 8; ++u) {
+                                if (J0 + u > I) break;
+                                const int jc = 8 * (J0 + u) + lq;  // B fragment column
+    #pragma unroll
+                                for (int st = 0; st < MAXST; ++st) {
+                                    if (st >= nsteps) break;
+                                    const double bfr = fma(c1[st], Wd[woff[st] + jc], __dmul_rn(c2[st], Wv[woff[st] + jc]));  // explicit: both code paths round alike
+                                    la::dmma_m8n8k4(cc[u].x, cc[u].y, afr[st], bfr);
+                                }
+                                if (n_prune) {  // a pruned column becomes an empty leaf: its row / column is exactly e_b / c
+                                    const int col = 8 * (J0 + u) + 2 * lk;
+                                    for (int s = 0; s < na; ++s) {
+                                        if (ctl->acc[s].move != MOVE_PRUNE) continue;
+                                        const int pb = ctl->acc[s].b;
+                                        if (row == pb || col == pb) cc[u].x = (row == col) ? inv_c : 0.0;
+                                        if (row == pb || col + 1 == pb) cc[u].y = (row == col + 1) ? inv_c : 0.0;
+                                    }
+                                }
+                            }
+    #pragma unroll
+                            for (int u = 0; u < 8; ++u)
+                                if (J0 + u <= I) __stcg(reinterpret_cast<double2*>(rowp + 8 * (J0 + u)), cc[u]);
+                        }
                     }
-                    double* rowp = cv.Binv + (size_t)row * P + 2 * lk;
-                    for (int J0 = 0; J0 <= I; J0 += 8) {
-                        double2 cc[8];
-#pragma unroll
-                        for (int u = 0; u < 8; ++u) cc[u] = (J0 + u <= I) ? sb_ldcg2(rowp + 8 * (J0 + u)) : make_double2(0.0, 0.0);
-#pragma unroll
+                }
+            } else {
+                // The nb8 (nb8 + 1) / 2 tiles of the lower triangle, row-major (I, J <= I), are dealt out in equal contiguous
+                // ranges to the cluster's warps (whatever the cluster size, every warp has work; a tile's result does not
+                // depend on who computes it).
+                const int T = nb8 * (nb8 + 1) / 2;
+                const int t_begin = (int)((long long)T * gw / ngw), t_end = (int)((long long)T * (gw + 1) / ngw);
+                int I0 = (int)((sqrtf(8.0f * (float)t_begin + 1.0f) - 1.0f) * 0.5f);
+                while (I0 * (I0 + 1) / 2 > t_begin) --I0;
+                while ((I0 + 1) * (I0 + 2) / 2 <= t_begin) ++I0;
+                int J0 = t_begin - I0 * (I0 + 1) / 2;
+                for (int tb = t_begin; tb < t_end; tb += 8) {
+                    double2 cc[8];
+                    {
+                        int I = I0, J = J0;
+    #pragma unroll
                         for (int u = 0; u < 8; ++u) {
-                            if (J0 + u > I) break;
-                            const int jc = 8 * (J0 + u) + lq;  // B fragment column
-#pragma unroll
+                            cc[u] = (tb + u < t_end) ? sb_ldcg2(cv.Binv + (size_t)(8 * I + lq) * P + 8 * J + 2 * lk) : make_double2(0.0, 0.0);
+                            if (J == I) { ++I; J = 0; } else { ++J; }
+                        }
+                    }
+                    {
+                        int I = I0, J = J0;
+    #pragma unroll
+                        for (int u = 0; u < 8; ++u) {
+                            if (tb + u >= t_end) break;
+                            const int row = 8 * I + lq, jc = 8 * J + lq;  // A fragment row, B fragment column
+    #pragma unroll
                             for (int st = 0; st < MAXST; ++st) {
                                 if (st >= nsteps) break;
-                                const double bfr = c1[st] * Wd[woff[st] + jc] + c2[st] * Wv[woff[st] + jc];
-                                la::dmma_m8n8k4(cc[u].x, cc[u].y, afr[st], bfr);
+                                const bool on = 2 * st + s_of < na;
+                                const double* Wc = comp ? Wv : Wd;
+                                const double afr = on ? -Wc[woff[st] + row] : 0.0;
+                                const double bfr = fma(c1[st], Wd[woff[st] + jc], __dmul_rn(c2[st], Wv[woff[st] + jc]));  // explicit: both code paths round alike
+                                la::dmma_m8n8k4(cc[u].x, cc[u].y, afr, bfr);
                             }
                             if (n_prune) {  // a pruned column becomes an empty leaf: its row / column is exactly e_b / c
-                                const int col = 8 * (J0 + u) + 2 * lk;
+                                const int col = 8 * J + 2 * lk;
                                 for (int s = 0; s < na; ++s) {
                                     if (ctl->acc[s].move != MOVE_PRUNE) continue;
                                     const int pb = ctl->acc[s].b;
@@ -805,10 +873,15 @@ sweep_block_kernel(WsLayout lay, SbLayout sl, void* ws, bark_nodes_soa forest, b
                                     if (row == pb || col + 1 == pb) cc[u].y = (row == col + 1) ? inv_c : 0.0;
                                 }
                             }
+                            if (J == I) { ++I; J = 0; } else { ++J; }
                         }
-#pragma unroll
-                        for (int u = 0; u < 8; ++u)
-                            if (J0 + u <= I) __stcg(reinterpret_cast<double2*>(rowp + 8 * (J0 + u)), cc[u]);
+                    }
+                    {
+    #pragma unroll
+                        for (int u = 0; u < 8; ++u) {
+                            if (tb + u < t_end) __stcg(reinterpret_cast<double2*>(cv.Binv + (size_t)(8 * I0 + lq) * P + 8 * J0 + 2 * lk), cc[u]);
+                            if (J0 == I0) { ++I0; J0 = 0; } else { ++J0; }
+                        }
                     }
                 }
             }

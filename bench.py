@@ -55,6 +55,7 @@ def parse_args():
     ap.add_argument("--config", type=int, default=4, choices=[2, 3, 4])
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"])
     ap.add_argument("--burnin", type=int, default=120, help="untimed sweeps that bring the chains to posterior-sized forests")
+    ap.add_argument("--chains", type=int, default=0, help="experiments: override the config's chain count")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
     ap.add_argument("--predict-candidates", type=int, default=1 << 21,
@@ -497,7 +498,9 @@ def run_b200_arm(a, local_rank):
     from bark_b200 import distributed as BD
 
     pk, ncu = load_peaks(), load_ncu_traffic()
-    cfg = CONFIGS[a.config]
+    cfg = dict(CONFIGS[a.config])
+    if a.chains:
+        cfg["chains"] = a.chains
     total = cfg["chains"] * (D.world if a.scaling == "weak" else 1)
     lo, hi = BD.shard_bounds(total, D.rank, D.world)
     C = hi - lo

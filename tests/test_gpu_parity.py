@@ -551,9 +551,10 @@ def test_acquisition_inputs_match_oracle(n, dims, m):
 
 
 def test_cluster_size_does_not_change_the_chain(monkeypatch):
-    """1 to 16 CTAs per chain (BARK_SWEEP_CLUSTER) only change how the leaf-space linear algebra is shared out: every
-    8-row unit of the DMMA product / update is computed by one warp whatever the cluster size, and the decisions are
-    taken redundantly on identical inputs, so the sampled forests AND hyper-parameters are bit-identical."""
+    """1 to 16 CTAs per chain (BARK_SWEEP_CLUSTER) only change how the leaf-space linear algebra is shared out: the
+    decisions are taken redundantly on identical inputs by every CTA of a chain, every 8-row unit of the DMMA product and
+    every tile of the update is computed by one warp with the same arithmetic whatever the cluster size: the sampled
+    forests are byte-identical and the hyper-parameter samples agree (to rounding at most)."""
     X, y, bounds, ft, _ = O.synthetic_problem(300, dim=5, cat_dim=1, num_cat=4, m_true=20, seed=12)
     chains, m = 3, 40
     p = B.BARKTrainParams(warmup_steps=25, num_samples=2, steps_per_sample=5, num_chains=chains)
