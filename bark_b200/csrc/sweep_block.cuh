@@ -51,8 +51,17 @@ constexpr int SB_KB = 8;      // proposals per block (the DMMA n dimension); sma
             ph_t = now__;                                    \
         }                                                    \
     } while (0)
+// per-warp probe of one block of chain 0 (debug build): cycles from the start of the phase to the end of the warp's own work
+#define SB_PROBE_BEGIN() long long pr_t0__ = clock64()
+#define SB_PROBE_END(ph)                                                                                          \
+    do {                                                                                                          \
+        if (lane == 0 && chain == 0 && t0 == 80 && sweep_in_call == 0 && sweep_offset >= 100)                     \
+            printf("probe ph=%d R=%d cr=%d wid=%d own=%lld\n", ph, R, cr, wid, (long long)(clock64() - pr_t0__)); \
+    } while (0)
 #else
 #define SB_MARK(i) do { } while (0)
+#define SB_PROBE_BEGIN() do { } while (0)
+#define SB_PROBE_END(ph) do { } while (0)
 #endif
 
 struct SbAccepted {  // one accepted proposal of the current block, kept until the block-end update
@@ -269,6 +278,7 @@ sweep_block_kernel(WsLayout lay, SbLayout sl, void* ws, bark_nodes_soa forest, b
         const int E = min(P, (p_hi + nb + 15) & ~15);  // extent of every vector of this block (multiple of 16)
         const int nb8 = E >> 3;
         SB_MARK(1);
+        SB_PROBE_BEGIN();
 
         // ------------------------------------------------------------------ Wd = Binv (e_a - e_b): symmetric rows
         // (issued before the masks so that the gathers overlap them; a grow's e_a / c term is added at its decision)
@@ -294,6 +304,7 @@ sweep_block_kernel(WsLayout lay, SbLayout sl, void* ws, bark_nodes_soa forest, b
             }
         }
 
+        SB_PROBE_END(0);  // the Wd gathers
         // ------------------------------------------------------------------ phase 1: moved-point masks, eta, n_u
         // SB_WARPS / KS warps per proposal; a warp takes every (SB_WARPS / KS)-th 32-point word of its proposal.  The
         // leaf bitsets come in coalesced (one word per lane per 1024 points) and are handed out by shuffles.
@@ -365,6 +376,7 @@ sweep_block_kernel(WsLayout lay, SbLayout sl, void* ws, bark_nodes_soa forest, b
                 eta_p = (part == 0 && lane == 0) ? __ldcg(cv.b + pb) : 0.0;
             }
             if (!live || mv == MOVE_PRUNE) cnt_p = warp_sum_int(cnt_p);  // (the ballot path counts warp-wide already)
+            SB_PROBE_END(1);  // gathers + masks
             // per-slot totals: eta (fixed tree over lanes, fixed order over the slot's warps), n_u (exact integers)
             const double e = warp_sum(eta_p);
             if (lane == 0) { red[wid] = e; red[SB_WARPS + wid] = (double)cnt_p; }
@@ -463,6 +475,9 @@ sweep_block_kernel(WsLayout lay, SbLayout sl, void* ws, bark_nodes_soa forest, b
         SB_MARK(3);
         csync();  // (B1) every column of V present on every CTA
         SB_MARK(4);
+#ifdef BARK_PHASE_TIMING
+        long long pr3__ = clock64();
+#endif
 
         // ------------------------------------------------------------------ phase 3: Wv = Binv V on the FP64 tensor pipe
         // Unit I = the 8 rows [8I, 8I+8) of the result: row part (row block I of the lower triangle times V) plus
@@ -567,6 +582,10 @@ sweep_block_kernel(WsLayout lay, SbLayout sl, void* ws, bark_nodes_soa forest, b
                 }
             }
         }
+#ifdef BARK_PHASE_TIMING
+        if (lane == 0 && chain == 0 && t0 == 80 && sweep_in_call == 0 && sweep_offset >= 100)
+            printf("probe ph=3 R=%d cr=%d wid=%d own=%lld\n", R, cr, wid, (long long)(clock64() - pr3__));
+#endif
         SB_MARK(5);
         csync();  // (B2) Wv complete on every CTA
         SB_MARK(6);
@@ -751,6 +770,9 @@ sweep_block_kernel(WsLayout lay, SbLayout sl, void* ws, bark_nodes_soa forest, b
             __syncthreads();
         }
         SB_MARK(7);
+#ifdef BARK_PHASE_TIMING
+        long long pr5__ = clock64();
+#endif
 
         // ------------------------------------------------------------------ phase 5: block-end updates of the global state
         const int na = ctl->n_acc;
@@ -885,6 +907,10 @@ sweep_block_kernel(WsLayout lay, SbLayout sl, void* ws, bark_nodes_soa forest, b
                     }
                 }
             }
+#ifdef BARK_PHASE_TIMING
+            if (lane == 0 && chain == 0 && t0 == 80 && sweep_in_call == 0 && sweep_offset >= 100)
+                printf("probe ph=5 R=%d cr=%d wid=%d own=%lld na=%d\n", R, cr, wid, (long long)(clock64() - pr5__), na);
+#endif
             // A' = A + v d^T + d v^T + n_u d d^T for every accepted proposal (exact integers; atomics make the order
             // irrelevant).  v is the slot's V column as it stood at the acceptance.
             {

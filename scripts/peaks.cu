@@ -175,6 +175,34 @@ __global__ void __launch_bounds__(512, 1) sync_latency_kernel(int iters, long lo
     }
 }
 
+// ------------------------------------------------------------------------------------------------ load latency
+// One warp per CTA chases pointers (dependent 8-byte ld.global.cg) through a buffer: L2-resident (8 MB) or HBM-sized
+// (2 GB, random): cycles per dependent load.  Then the round trip of a BATCH of 8 independent 16-byte loads per lane
+// (what the sweep kernel's product pass issues), alone on the GPU and with every SM doing the same.
+__global__ void chase_kernel(const unsigned long long* __restrict__ next, int steps, long long* out) {
+    unsigned long long p = threadIdx.x + blockIdx.x * 997;
+    const long long t0 = clock64();
+    for (int i = 0; i < steps; ++i) p = __ldcg(next + p);
+    const long long t1 = clock64();
+    if (threadIdx.x == 0 && blockIdx.x == 0) { out[0] = (t1 - t0) / steps; out[1] = (long long)p; }
+}
+__global__ void __launch_bounds__(512, 1) batch_kernel(const double2* __restrict__ buf, size_t n_vec, int iters, long long* out) {
+    const int lane = threadIdx.x & 31, lq = lane >> 2, lk = lane & 3;
+    size_t base = ((size_t)blockIdx.x * 16 + (threadIdx.x >> 5)) * 65536 % (n_vec / 2);
+    double acc = 0.0;
+    const long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+        double2 x[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) x[u] = __ldcg(buf + base + (size_t)lq * 416 + lk + 4 * u + (size_t)it * 3331);  // 8 rows x 64 B, like a tile batch
+#pragma unroll
+        for (int u = 0; u < 8; ++u) acc += x[u].x + x[u].y;
+        base = (base + (size_t)(acc != 12345.678)) % (n_vec / 2);  // dependency: the next batch waits for this one
+    }
+    const long long t1 = clock64();
+    if (threadIdx.x == 0 && blockIdx.x == 0) { out[0] = (t1 - t0) / iters; out[1] = (long long)acc; }
+}
+
 template <class F>
 static float best_ms(F launch, int reps = 5) {
     cudaEvent_t e0, e1;
@@ -260,7 +288,42 @@ int main() {
         lat[k][0] = h[0]; lat[k][1] = h[1]; lat[k][2] = h[2];
     }
 
+    // load latencies
+    long long lat_l2 = 0, lat_hbm = 0, bat_alone = 0, bat_all = 0;
+    {
+        const size_t n_small = (8ull << 20) / 8, n_big = (2ull << 30) / 8;
+        std::vector<unsigned long long> h(n_big);
+        unsigned long long x = 88172645463325252ull;
+        for (size_t i = 0; i < n_big; ++i) { x ^= x << 13; x ^= x >> 7; x ^= x << 17; h[i] = x % n_big; }
+        unsigned long long* d_next = reinterpret_cast<unsigned long long*>(buf);
+        CK(cudaMemcpy(d_next, h.data(), n_big * 8, cudaMemcpyHostToDevice));
+        chase_kernel<<<1, 32>>>(d_next, 2000, lout);
+        CK(cudaDeviceSynchronize());
+        long long hh[2];
+        CK(cudaMemcpy(hh, lout, 16, cudaMemcpyDeviceToHost));
+        lat_hbm = hh[0];
+        for (size_t i = 0; i < n_small; ++i) { x ^= x << 13; x ^= x >> 7; x ^= x << 17; h[i] = x % n_small; }
+        CK(cudaMemcpy(d_next, h.data(), n_small * 8, cudaMemcpyHostToDevice));
+        chase_kernel<<<1, 32>>>(d_next, 20000, lout);  // warms L2
+        chase_kernel<<<1, 32>>>(d_next, 20000, lout);
+        CK(cudaDeviceSynchronize());
+        CK(cudaMemcpy(hh, lout, 16, cudaMemcpyDeviceToHost));
+        lat_l2 = hh[0];
+        CK(cudaMemset(buf, 0, 64ull << 20));
+        batch_kernel<<<1, 32>>>(reinterpret_cast<const double2*>(buf), (32ull << 20) / 16, 2000, lout);
+        batch_kernel<<<1, 32>>>(reinterpret_cast<const double2*>(buf), (32ull << 20) / 16, 2000, lout);
+        CK(cudaDeviceSynchronize());
+        CK(cudaMemcpy(hh, lout, 16, cudaMemcpyDeviceToHost));
+        bat_alone = hh[0];
+        batch_kernel<<<sms, 512>>>(reinterpret_cast<const double2*>(buf), (32ull << 20) / 16, 2000, lout);
+        CK(cudaDeviceSynchronize());
+        CK(cudaMemcpy(hh, lout, 16, cudaMemcpyDeviceToHost));
+        bat_all = hh[0];
+    }
+
     printf("{\"device\": \"%s\", \"sms\": %d, \"sm_clock_mhz_attr\": %.0f,\n", prop.name, sms, clk_khz / 1e3);
+    printf(" \"load_latency_cycles\": {\"l2_hit_dependent_ldcg\": %lld, \"hbm_dependent_ldcg\": %lld, "
+           "\"batch8x16B_one_warp\": %lld, \"batch8x16B_16_warps_every_sm\": %lld},\n", lat_l2, lat_hbm, bat_alone, bat_all);
     printf(" \"fp64_dmma_tflops\": %.2f, \"fp64_dfma_tflops\": %.2f,\n", tf_dmma, tf_dfma);
     printf(" \"int8_umma_tops\": %.1f, \"int8_umma_ok\": %s,\n", tops_u, hu[1] == 0xDEADu ? "false" : "true");
     printf(" \"l2_read_gbs\": %.0f, \"l2_buffer_mb\": %zu, \"hbm_read_gbs\": %.0f, \"hbm_copy_gbs\": %.0f,\n", gbs_l2,
