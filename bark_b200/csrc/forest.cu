@@ -93,23 +93,12 @@ constexpr int TRAV_STAGE = 32;      // node slots staged per tree; a walk that r
 // Posterior trees use the lowest slots (a grow takes the first two inactive slots, src/bark/fitting/tree_proposals.py:45-58;
 // SURVEY: <= 9 of 100 slots active), so only slots [0, TRAV_STAGE) of every tree are staged: 1/3 of the node bytes of a
 // full 100-slot stage, which otherwise outweigh the leaf ids the CTA writes.  Slots beyond the stage stay reachable.
-__device__ __forceinline__ uint32_t walk_tree_staged(const WalkNode* __restrict__ wn, int staged, const bark_nodes_soa& nodes,
-                                                     int64_t gbase, const double* __restrict__ xp, int xstride,
-                                                     const int* __restrict__ ft, int node_limit) {
-    uint32_t at = 0;
-    for (int it = 0; it < node_limit; ++it) {
-        WalkNode nd;
-        if ((int)at < staged) {
-            nd = wn[at];
-        } else {
-            const int64_t g = gbase + at;
-            nd = make_walk_node(nodes.is_leaf[g], nodes.feature[g], nodes.threshold[g], nodes.left[g], nodes.right[g]);
-        }
-        if (nd.feat_leaf & 0x8000u) return at;
-        const int f = nd.feat_leaf & 0x7fffu;
-        at = goes_left(xp[(size_t)f * xstride], nd.thr, ft[f]) ? nd.left : nd.right;
-    }
-    return at;
+// One node of a tree: the staged copy, or (slots beyond the stage) the global record.
+__device__ __forceinline__ WalkNode load_walk_node(const WalkNode* __restrict__ wn, int staged, const bark_nodes_soa& nodes, int64_t gbase,
+                                                   uint32_t at) {
+    if ((int)at < staged) return wn[at];
+    const int64_t g = gbase + at;
+    return make_walk_node(nodes.is_leaf[g], nodes.feature[g], nodes.threshold[g], nodes.left[g], nodes.right[g]);
 }
 
 __global__ void __launch_bounds__(TRAV_THREADS)
@@ -117,11 +106,12 @@ traverse_kernel(bark_nodes_soa nodes, int64_t m, int node_limit, const double* _
                 int d, const int32_t* __restrict__ feat_types, uint32_t* __restrict__ leaves) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // layout: WalkNode wn[TRAV_TREES][staged] | double xs[d][TRAV_THREADS+1] (feature-major, padded)
-    //         | int ft[d] | uint32 out[TRAV_THREADS][TRAV_TREES+1]
+    //         | float xf[d][TRAV_THREADS+1] | int ft[d] | uint32 out[TRAV_THREADS][TRAV_TREES+1]
     const int staged = min(node_limit, TRAV_STAGE);
     WalkNode* wn = reinterpret_cast<WalkNode*>(smem_raw);
     double* xs = reinterpret_cast<double*>(wn + (size_t)TRAV_TREES * staged);
-    int* ft = reinterpret_cast<int*>(xs + (size_t)d * (TRAV_THREADS + 1));
+    float* xf = reinterpret_cast<float*>(xs + (size_t)d * (TRAV_THREADS + 1));
+    int* ft = reinterpret_cast<int*>(xf + (size_t)(((size_t)d * (TRAV_THREADS + 1) + 1) & ~(size_t)1));
     uint32_t* outs = reinterpret_cast<uint32_t*>(ft + ((d + 1) & ~1));  // [TRAV_THREADS][TRAV_TREES + 1]
 
     const int64_t forest = blockIdx.z;
@@ -137,20 +127,58 @@ traverse_kernel(bark_nodes_soa nodes, int64_t m, int node_limit, const double* _
         const int64_t g = node_base + (int64_t)t * node_limit + sl;
         wn[e] = make_walk_node(nodes.is_leaf[g], nodes.feature[g], nodes.threshold[g], nodes.left[g], nodes.right[g]);
     }
+    bool any_cat = false;
     for (int e = threadIdx.x; e < d; e += TRAV_THREADS) ft[e] = feat_types[e];
-    // stage X tile: rows p0..p0+np are contiguous (np*d doubles) -> coalesced; store feature-major
+    for (int e = 0; e < d; ++e) any_cat |= (feat_types[e] == FEAT_CAT);  // CTA-uniform
+    // stage X tile: rows p0..p0+np are contiguous (np*d doubles) -> coalesced; store feature-major.  Numeric splits are
+    // decided in FP32 on the candidates rounded UP: x <= (double)thr with an f32 threshold  <=>  ru_f32(x) <= thr -- the
+    // reference's comparison (src/bark/forest.py:33-47) bit for bit, off the FP64 pipe.
     for (int e = threadIdx.x; e < np * d; e += TRAV_THREADS) {
         const int p = e / d, f = e % d;
-        xs[(size_t)f * (TRAV_THREADS + 1) + p] = X[p0 * d + e];
+        const double x = X[p0 * d + e];
+        xs[(size_t)f * (TRAV_THREADS + 1) + p] = x;
+        xf[(size_t)f * (TRAV_THREADS + 1) + p] = __double2float_ru(x);
     }
     __syncthreads();
 
     if ((int)threadIdx.x < np) {
         const double* xp = xs + threadIdx.x;
-        for (int t = 0; t < nt; ++t) {
-            outs[threadIdx.x * (TRAV_TREES + 1) + t] = walk_tree_staged(wn + (size_t)t * staged, staged, nodes,
-                                                                        node_base + (int64_t)t * node_limit, xp,
-                                                                        TRAV_THREADS + 1, ft, node_limit);
+        const float* xfp = xf + threadIdx.x;
+        // four trees in flight per thread, branch-free (a leaf steps to itself): the four pointer chases overlap
+        for (int t = 0; t < nt; t += 4) {
+            WalkNode nd[4];
+            uint32_t cur[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int tu = min(t + u, nt - 1);
+                cur[u] = 0;
+                nd[u] = wn[(size_t)tu * staged];
+            }
+            for (int it = 0; it < node_limit; ++it) {
+                if ((nd[0].feat_leaf & nd[1].feat_leaf & nd[2].feat_leaf & nd[3].feat_leaf) & 0x8000u) break;
+                float xv[4];
+                int fi[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    fi[u] = min((int)(nd[u].feat_leaf & 0x7fffu), d - 1);  // (a leaf's feature bits are ignored below)
+                    xv[u] = xfp[(size_t)fi[u] * (TRAV_THREADS + 1)];
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    bool left = xv[u] <= nd[u].thr;
+                    if (any_cat && ft[fi[u]] == FEAT_CAT) left = goes_left(xp[(size_t)fi[u] * (TRAV_THREADS + 1)], nd[u].thr, FEAT_CAT);
+                    const uint32_t at = min((uint32_t)(left ? nd[u].left : nd[u].right), (uint32_t)(node_limit - 1));
+                    cur[u] = (nd[u].feat_leaf & 0x8000u) ? cur[u] : at;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int tu = min(t + u, nt - 1);
+                    nd[u] = load_walk_node(wn + (size_t)tu * staged, staged, nodes, node_base + (int64_t)tu * node_limit, cur[u]);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (t + u < nt) outs[threadIdx.x * (TRAV_TREES + 1) + t + u] = cur[u];
         }
     }
     __syncthreads();
@@ -202,6 +230,7 @@ int bark_traverse(bark_nodes_soa nodes, int64_t n_forests, int64_t m, int64_t no
     BARK_CHECK_ARG(n_forests <= 65535 && ceil_div(m, TRAV_TREES) <= 65535, "grid too large");
     size_t smem = (size_t)TRAV_TREES * std::min<int64_t>(node_limit, TRAV_STAGE) * sizeof(WalkNode) +
                   (size_t)d * (TRAV_THREADS + 1) * sizeof(double) +
+                  (((size_t)d * (TRAV_THREADS + 1) + 1) & ~(size_t)1) * sizeof(float) +
                   (size_t)((d + 1) & ~1) * sizeof(int) + (size_t)TRAV_THREADS * (TRAV_TREES + 1) * sizeof(uint32_t);
     BARK_CHECK_ARG(smem <= 220 * 1024, "d * node_limit too large for the shared-memory staging");
     BARK_CUDA(cudaFuncSetAttribute(traverse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -1,16 +1,22 @@
 // a14 on the tensor cores: posterior-predictive variance as an EXACT int8-sliced one-hot GEMM.
 //
 //   var_s(x) = sig_s * z^T Binv_s z,   z = one-hot leaf indicator of the candidate (m ones among P columns).
-// Binv_s is turned once per posterior sample into 7 signed base-256 digit planes of a 54-bit fixed-point
-// representation (|Binv| <= 1/c bounds the scale):  Binv = 2^-shift * sum_k 256^k D_k,  D_k int8.
-// For a tile of 128 candidates the CTA walks the trees with three threads per candidate (leaf columns collected as
-// a bit mask per row, mean = sum_t w[col_t] on the way), expands the masks into the one-hot int8 A operand in
-// shared memory, then T_k = Zc * D_k runs on tcgen05 (kind::i8, s32 accumulators in TMEM, M = 128, N = 256 per
-// instruction: with both operands in shared memory a small N is bound by re-reading A), one (column tile, digit
-// plane) item at a time into one of two 256-column TMEM buffers, the digit tiles streamed by the bulk-copy engine.
-// The epilogue never needs T itself: z^T Binv z = sum_k 256^k * (sum over the candidate's own columns of T_k),
-// i.e. 7 masked int32 row sums (exact), combined once in FP64; it drains one TMEM buffer while the tensor core
-// fills the other.  No n_c x P matrix ever exists in memory.
+// Binv_s is turned once per posterior sample into 7 signed base-256 digit planes of a fixed-point representation
+// (|Binv| <= 1/c bounds the scale) of the triangle { diag, 2 x strictly lower }:  z^T Binv z = 2^-shift * sum_k 256^k z^T D_k z.
+//
+// One persistent CTA per tile of 128 candidates loops over the posterior samples; its warps have fixed roles that run
+// concurrently, one sample apart:
+//   walkers (12 warps)   stage the sample's trees, walk them with three threads per candidate (four trees in flight per
+//                        thread), leaf columns -> the row's bit mask, partial means on the way;
+//   epilogue (8 warps)   expand the masks into the one-hot int8 A operand (K-major, SWIZZLE_128B) once the previous
+//                        sample's MMAs are done; drain the accumulators: z^T D_k z is the masked row sum of T_k = Z D_k,
+//                        read as packed int16 pairs (tcgen05.ld .pack::16b) and reduced with dp2a against the mask bytes;
+//   MMA issuer (1 thread) tcgen05.mma kind::i8, M = 128, N = 256 (N = 128 runs at half rate: scripts/umma_shapes.cu), one
+//                        (column tile, digit plane) item at a time into one of two 256-column TMEM accumulators, only
+//                        the K tiles on or below the diagonal band;
+//   producer (1 thread)  streams the digit tiles with the bulk-copy engine through a shared-memory ring, free-running
+//                        across samples.
+// The walk of sample s + 1 overlaps the MMAs of sample s.  No n_c x P matrix ever exists in memory.
 //
 // Replaces  scale - diag(K_xX K^-1 K_Xx)  of src/bark/tree_kernels/tree_gps.py:103-112.
 #include <algorithm>
@@ -26,12 +32,14 @@ constexpr int PU_N = 256;           // Binv columns per accumulator tile (UMMA N
 constexpr int PU_KB = 128;          // K bytes per operand tile (one SWIZZLE_128B atom row)
 constexpr int PU_SLICES = 7;        // base-256 digit planes
 constexpr int PU_MAX_STAGES = 4;    // ring stages; one stage = one K tile of one (column tile, digit plane)
-constexpr int PU_WALK_GROUPS = 4;   // threads per candidate: walk (trees t = g mod 4) and epilogue (column chunks j = g mod 4);
-                                    // 6 groups measured the same (the walk is issue / LSU bound, not latency bound)
-constexpr int PU_THREADS = 64 + 128 * PU_WALK_GROUPS;  // warps 0-3 and 6..: walk + epilogue groups, 4: MMA issue, 5: TMA producer
+constexpr int PU_WALK_GROUPS = 3;   // walker threads per candidate (trees t = g mod 3)
+constexpr int PU_WALK_WARPS = 4 * PU_WALK_GROUPS;
+constexpr int PU_EPI_WARPS = 8;     // two per TMEM lane quarter: each takes 128 of an item's 256 columns
+constexpr int PU_FIRST_EPI = 2, PU_FIRST_WALK = PU_FIRST_EPI + PU_EPI_WARPS;  // warp 0: MMA issue, warp 1: bulk-copy producer
+constexpr int PU_THREADS = 32 * (PU_FIRST_WALK + PU_WALK_WARPS);
 constexpr int PU_A_TILE = PU_ROWS * PU_KB;  // 16 KB
 constexpr int PU_B_TILE = PU_N * PU_KB;     // 32 KB
-constexpr int PU_RING_MAX = 128 * 1024;
+constexpr int PU_RING_MAX = PU_MAX_STAGES * PU_B_TILE;
 constexpr int PU_MAX_P = 768;
 
 __device__ __forceinline__ uint32_t pu_smem(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -39,6 +47,9 @@ __host__ __device__ __forceinline__ uint32_t pu_swizzle(uint32_t r, uint32_t kb)
     const uint32_t g = r >> 3, rr = r & 7, chunk = kb >> 4, b = kb & 15;
     return g * 1024u + rr * 128u + ((chunk ^ rr) << 4) + b;
 }
+
+// First K tile of column tile nt that can hold an entry of the triangle k >= q (columns q of tile nt start at nt * PU_N).
+__host__ __device__ __forceinline__ int pu_kt_lo(int nt) { return nt * (PU_N / PU_KB); }
 
 struct PrepLayout {
     size_t off_table, off_tiles, off_scale, total;
@@ -70,7 +81,8 @@ __global__ void pu_table_kernel(WsLayout lay, const void* ws, bark_nodes_soa for
     }
 }
 
-// Binv (lower triangle current) -> 7 digit planes, tiled [sample][nt][slice][kt] and pre-swizzled (K-major SW128)
+// Binv (lower triangle current) -> 7 digit planes, tiled [sample][nt][slice][kt] and pre-swizzled (K-major SW128);
+// only the K tiles kt >= pu_kt_lo(nt) of a column tile are written and later streamed
 __global__ void pu_slice_kernel(WsLayout lay, const void* ws, int kt_n, int nt_n, uint8_t* __restrict__ tiles,
                                 double* __restrict__ scale_out) {
     const int64_t sample = blockIdx.y;
@@ -85,10 +97,13 @@ __global__ void pu_slice_kernel(WsLayout lay, const void* ws, int kt_n, int nt_n
     uint8_t* base = tiles + (size_t)sample * nt_n * PU_SLICES * kt_n * PU_B_TILE;
     for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < Q * K; idx += (int64_t)gridDim.x * blockDim.x) {
         const int64_t q = idx / K, k = idx % K;
-        double v = 0.0;
-        if (q < P && k < P) v = (k <= q) ? cv.Binv[q * P + k] : cv.Binv[k * P + q];
-        long long x = llrint(ldexp(v, shift));
         const int64_t nt = q / PU_N, kt = k / PU_KB;
+        if (kt < pu_kt_lo((int)nt)) continue;  // tile above the diagonal band: never loaded
+        // z^T Binv z = sum_i Binv_ii z_i + 2 sum_{k > q} Binv_kq z_k z_q: the operand is the triangle k >= q with the
+        // off-diagonal entries doubled (|2 Binv_kq| < 2^(e+1): 55 signed bits, inside the 7 balanced digits' +-2^55)
+        double v = 0.0;
+        if (q < P && k < P && k >= q) v = (k == q) ? cv.Binv[q * P + q] : 2.0 * cv.Binv[k * P + q];
+        long long x = llrint(ldexp(v, shift));
         const uint32_t off = pu_swizzle((uint32_t)(q % PU_N), (uint32_t)(k % PU_KB));
 #pragma unroll
         for (int s = 0; s < PU_SLICES; ++s) {
@@ -133,6 +148,28 @@ __device__ __forceinline__ void pu_mbar_wait(uint64_t* bar, uint32_t parity, uns
         }
     }
 }
+// Latency-critical hand-offs (accumulator full / free) poll with the non-suspending test_wait: try_wait may park the
+// thread for a hardware-chosen interval before it re-checks.
+__device__ __forceinline__ void pu_mbar_spin(uint64_t* bar, uint32_t parity, unsigned* status) {
+    unsigned spins = 0;
+    for (;;) {
+        uint32_t ok;
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.b32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(ok)
+            : "r"(pu_smem(bar)), "r"(parity)
+            : "memory");
+        if (ok) break;
+        if (++spins > (1u << 28)) {
+            atomicOr(status, BARK_ST_TIMEOUT);
+            break;
+        }
+    }
+}
 __device__ __forceinline__ void pu_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(pu_smem(dst)),
                  "l"(src), "r"(bytes), "r"(pu_smem(bar))
@@ -168,25 +205,40 @@ __device__ __forceinline__ void pu_tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) 
           "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
         : "r"(taddr)
         : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+// 64 accumulator columns as 32 registers: .pack::16b keeps the low 16 bits of two adjacent 32-bit columns (|T| <= 128 m fits
+// int16 for m <= 255 trees; larger forests take the 32-bit path)
+__device__ __forceinline__ void pu_tmem_ld64_pack16(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.pack::16b.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void pu_tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 struct PuSmem {
-    size_t off_a, off_ring, off_table, off_zmask, off_w, off_xs, off_ft, off_mean, off_part, off_bars, total;
+    size_t off_a, off_ring, off_table, off_zmask, off_w, off_xs, off_xf, off_ft, off_mean, off_part, off_bars, total;
 };
-__host__ __device__ inline PuSmem pu_smem_layout(int m, int hi, int d, int kt, int ring_bytes) {
+__host__ __device__ inline PuSmem pu_smem_layout(int m, int hi, int d, int kt, int ring_bytes, int nb) {
     PuSmem s;
     size_t o = 0;
     s.off_a = o;      o += (size_t)kt * PU_A_TILE;
     s.off_ring = o;   o += (size_t)ring_bytes;
     s.off_table = o;  o = align256(o + (size_t)m * hi * sizeof(WalkNode));
-    s.off_zmask = o;  o = align256(o + (size_t)PU_ROWS * kt * 2 * 8);  // [64-column word][row]
+    s.off_zmask = o;  o = align256(o + (size_t)nb * PU_ROWS * kt * 2 * 8);  // [mask buffer][64-column word][row]
     s.off_w = o;      o = align256(o + (size_t)kt * PU_KB * 8);
     s.off_xs = o;     o = align256(o + (size_t)d * (PU_ROWS + 1) * 8);
+    s.off_xf = o;     o = align256(o + (size_t)d * (PU_ROWS + 1) * 4);
     s.off_ft = o;     o = align256(o + (size_t)d * 4);
-    s.off_mean = o;   o = align256(o + (size_t)PU_WALK_GROUPS * PU_ROWS * 8);
-    s.off_part = o;   o = align256(o + (size_t)(PU_WALK_GROUPS - 1) * PU_SLICES * PU_ROWS * 4);
-    s.off_bars = o;   o = align256(o + (size_t)(2 * PU_MAX_STAGES + 4) * 8 + 16);
+    s.off_mean = o;   o = align256(o + (size_t)nb * PU_WALK_GROUPS * PU_ROWS * 8);  // [mask buffer][group][row]
+    s.off_part = o;   o = align256(o + (size_t)PU_SLICES * PU_ROWS * 4);           // second column half's row sums
+    s.off_bars = o;   o = align256(o + (size_t)(2 * PU_MAX_STAGES + 9) * 8 + 16);
     s.total = o;
     return s;
 }
@@ -201,217 +253,357 @@ __device__ __forceinline__ uint4 pu_expand16(uint32_t b) {
     return r;
 }
 
+#ifdef BARK_PHASE_TIMING
+// per-role wait / work cycle totals of one CTA in the middle of the grid (debug build only)
+#define PU_T0() do { pu_c = clock64(); } while (0)
+#define PU_ACC(i) do { long long t_ = clock64(); pu_w[i] += t_ - pu_c; pu_c = t_; } while (0)
+#define PU_REPORT(...) do { if (blockIdx.x == gridDim.x / 2 && blockIdx.y == 0) printf(__VA_ARGS__); } while (0)
+#else
+#define PU_T0() do { } while (0)
+#define PU_ACC(i) do { } while (0)
+#define PU_REPORT(...) do { } while (0)
+#endif
+
+__device__ __forceinline__ void pu_named_sync(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
+
 __global__ void __launch_bounds__(PU_THREADS, 1)
 predict_umma_kernel(WsLayout lay, const void* ws, const WalkNode* __restrict__ table, const uint8_t* __restrict__ tiles,
-                    const double* __restrict__ scales, int hi, int kt_n, int nt_n, int ring_bytes,
+                    const double* __restrict__ scales, int hi, int kt_n, int nt_n, int ring_bytes, int nb,
                     const double* __restrict__ cand,
                     int64_t n_c, double* __restrict__ mu, double* __restrict__ var) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     const int d = (int)lay.d, m = (int)lay.m;
-    const PuSmem sl = pu_smem_layout(m, hi, d, kt_n, ring_bytes);
+    const PuSmem sl = pu_smem_layout(m, hi, d, kt_n, ring_bytes, nb);  // nb = 2: the walk runs one sample ahead; 1: tight shared memory
     unsigned char* a_tiles = smem_raw + sl.off_a;
     unsigned char* ring = smem_raw + sl.off_ring;
     WalkNode* tb = reinterpret_cast<WalkNode*>(smem_raw + sl.off_table);
-    unsigned long long* zmask = reinterpret_cast<unsigned long long*>(smem_raw + sl.off_zmask);  // [word][row]
+    unsigned long long* zmask = reinterpret_cast<unsigned long long*>(smem_raw + sl.off_zmask);  // [parity][word][row]
     double* w_s = reinterpret_cast<double*>(smem_raw + sl.off_w);
     double* xs = reinterpret_cast<double*>(smem_raw + sl.off_xs);  // [d][PU_ROWS + 1]
+    float* xf = reinterpret_cast<float*>(smem_raw + sl.off_xf);    // [d][PU_ROWS + 1]: candidates rounded UP to f32
     int* ftc = reinterpret_cast<int*>(smem_raw + sl.off_ft);
-    double* meanp = reinterpret_cast<double*>(smem_raw + sl.off_mean);  // [group][row]
-    int* accp = reinterpret_cast<int*>(smem_raw + sl.off_part);          // [group - 1][slice][row]
+    double* meanp = reinterpret_cast<double*>(smem_raw + sl.off_mean);  // [parity][group][row]
+    int* accp = reinterpret_cast<int*>(smem_raw + sl.off_part);          // [slice][row]
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_raw + sl.off_bars);
     uint64_t* empty_bar = full_bar + PU_MAX_STAGES;
-    uint64_t* acc_full = empty_bar + PU_MAX_STAGES;  // [2]
-    uint64_t* acc_free = acc_full + 2;               // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_free + 2);
+    uint64_t* acc_full = empty_bar + PU_MAX_STAGES;  // [2] MMA -> epilogue
+    uint64_t* acc_free = acc_full + 2;               // [2] epilogue -> MMA
+    uint64_t* mask_ready = acc_free + 2;             // [2] walkers -> epilogue: masks / partial means of a sample complete
+    uint64_t* mask_free = mask_ready + 2;            // [2] epilogue -> walkers: the sample that used the buffer is finished
+    uint64_t* a_ready = mask_free + 2;               // [1] epilogue -> MMA: the A operand of the next sample is in place
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_ready + 1);
     const int nstages = min(PU_MAX_STAGES, ring_bytes / PU_B_TILE);
     const int nwords = kt_n * 2;  // 64-column mask words per candidate row
+    const int mask_words = PU_ROWS * nwords;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int64_t sample = blockIdx.y;
+#ifdef BARK_PHASE_TIMING
+    long long pu_w[6] = {0, 0, 0, 0, 0, 0}, pu_c = 0;
+#endif
     const int64_t p0 = (int64_t)blockIdx.x * PU_ROWS;
     const int np = (int)min((int64_t)PU_ROWS, n_c - p0);
-    ChainView cv = chain_view(lay, const_cast<void*>(ws), sample);
-    unsigned* pu_status = &cv.sc->status;  // bounded pipeline waits flag BARK_ST_TIMEOUT here
+    // samples of this CTA: gridDim.y splits them when there are fewer candidate tiles than SMs
+    const int64_t S = lay.chains;
+    const int64_t s_lo = S * blockIdx.y / gridDim.y, s_hi = S * (blockIdx.y + 1) / gridDim.y;
+    const int ns = (int)(s_hi - s_lo);
     SharedView sv = shared_view(lay, ws);
 
-    // ---- setup: barriers, TMEM, staging of the sample's trees / w and of the candidate tile
+    // ---- setup: barriers, TMEM, the candidate tile
     if (tid == 0) {
         for (int s = 0; s < PU_MAX_STAGES; ++s) { pu_mbar_init(full_bar + s, 1); pu_mbar_init(empty_bar + s, 1); }
-        for (int b = 0; b < 2; ++b) { pu_mbar_init(acc_full + b, 1); pu_mbar_init(acc_free + b, PU_ROWS * PU_WALK_GROUPS); }
+        for (int b = 0; b < 2; ++b) {
+            pu_mbar_init(acc_full + b, 1);
+            pu_mbar_init(acc_free + b, PU_EPI_WARPS);
+            pu_mbar_init(mask_ready + b, PU_WALK_WARPS);
+            pu_mbar_init(mask_free + b, PU_EPI_WARPS);
+        }
+        pu_mbar_init(a_ready, PU_EPI_WARPS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 4) {
+    if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(pu_smem(tmem_slot)), "r"(512u)
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    {
-        const WalkNode* src = table + (size_t)sample * m * hi;
-        for (int e = tid; e < m * hi; e += PU_THREADS) tb[e] = src[e];
-        for (int e = tid; e < kt_n * PU_KB; e += PU_THREADS) w_s[e] = (e < lay.P) ? cv.w[e] : 0.0;
-        for (int e = tid; e < np * d; e += PU_THREADS) xs[(size_t)(e % d) * (PU_ROWS + 1) + e / d] = cand[p0 * d + e];
-        for (int e = tid; e < d; e += PU_THREADS) ftc[e] = sv.ft[e];
-        for (int e = tid; e < PU_ROWS * nwords; e += PU_THREADS) zmask[e] = 0ull;
+    bool any_cat = false;
+    // x <= (double)thr with an f32 threshold  <=>  ru_f32(x) <= thr  (ru = the smallest f32 >= x): the numeric splits are
+    // decided in FP32 -- exactly as the reference's comparison -- and keep the walk off the FP64 pipe
+    for (int e = tid; e < np * d; e += PU_THREADS) {
+        const double x = cand[p0 * d + e];
+        xs[(size_t)(e % d) * (PU_ROWS + 1) + e / d] = x;
+        xf[(size_t)(e % d) * (PU_ROWS + 1) + e / d] = __double2float_ru(x);
     }
-    // ---- warp 5: TMA producer.  One stage = one K tile (n_cols x 128 B) of one (column tile, digit plane) item.
-    // The first ring-full needs no free-slot wait: it is issued now, concurrently with the walk (the digit stream
-    // does not depend on the candidates).
-    const uint8_t* src_tiles = tiles + (size_t)sample * nt_n * PU_SLICES * kt_n * PU_B_TILE;
-    const int items = nt_n * PU_SLICES;
-    const int loads = items * kt_n;  // global tile index == load index: tiles are stored [nt][slice][kt]
-    const int last_cols = kt_n * PU_KB - (nt_n - 1) * PU_N;  // columns of the last column tile (128 or 256)
-    __syncthreads();  // barriers initialised
-    if (warp == 5 && lane == 0) {
-        for (int ld = 0; ld < nstages && ld < loads; ++ld) {
-            const int nt = ld / (PU_SLICES * kt_n);
-            const uint32_t bytes = (uint32_t)((nt == nt_n - 1) ? last_cols : PU_N) * PU_KB;
-            pu_mbar_expect_tx(full_bar + ld, bytes);
-            pu_bulk_g2s(ring + (size_t)ld * PU_B_TILE, src_tiles + (size_t)ld * PU_B_TILE, bytes, full_bar + ld);
-        }
-    }
-
-    // ---- walk: PU_WALK_GROUPS threads per candidate (group g takes the trees t = g mod groups): leaf columns into
-    // the row's bit mask, partial means per group
-    const int wg = (warp < 4) ? 0 : (warp >= 6 ? 1 + (warp - 6) / 4 : -1);  // walk / epilogue group of this warp
-    {
-        const int row = (warp < 4) ? tid : (warp >= 6 ? (tid - 6 * 32) % PU_ROWS : 0);
-        if (wg >= 0) {
-            double mean = 0.0;
-            if (row < np) {
-                const double* xp = xs + row;
-                for (int t = wg; t < m; t += PU_WALK_GROUPS) {
-                    const WalkNode* wn = tb + (size_t)t * hi;
-                    WalkNode nd = wn[0];
-                    for (int it = 0; it < hi && !(nd.feat_leaf & 0x8000u); ++it) {
-                        const int f = nd.feat_leaf & 0x7fffu;
-                        const uint32_t at = goes_left(xp[(size_t)f * (PU_ROWS + 1)], nd.thr, ftc[f]) ? nd.left : nd.right;
-                        nd = wn[min(at, (uint32_t)(hi - 1))];
-                    }
-                    const int col = __float_as_int(nd.thr);
-                    mean += w_s[col];
-                    atomicOr(zmask + (size_t)(col >> 6) * PU_ROWS + row, 1ull << (col & 63));
-                }
-            }
-            meanp[wg * PU_ROWS + row] = mean;
-        }
-    }
-    __syncthreads();
-    // ---- one-hot A operand (K-major, SWIZZLE_128B) from the masks: one 16-byte chunk per thread and step
-    {
-        const int chunks_per_row = kt_n * 8;
-        for (int e = tid; e < PU_ROWS * chunks_per_row; e += PU_THREADS) {
-            const int row = e / chunks_per_row, ch = e % chunks_per_row;
-            const uint32_t bits = (uint32_t)(zmask[(size_t)(ch >> 2) * PU_ROWS + row] >> ((ch & 3) * 16)) & 0xFFFFu;
-            const uint32_t r = (uint32_t)row, c = (uint32_t)(ch & 7);
-            unsigned char* dst = a_tiles + (size_t)(ch >> 3) * PU_A_TILE + (r >> 3) * 1024u + (r & 7) * 128u + ((c ^ (r & 7)) << 4);
-            *reinterpret_cast<uint4*>(dst) = pu_expand16(bits);
-        }
-    }
-    asm volatile("fence.proxy.async;" ::: "memory");  // generic writes of the A operand -> tensor-core (async proxy) reads
+    for (int e = tid; e < d; e += PU_THREADS) ftc[e] = sv.ft[e];
+    for (int e = 0; e < d; ++e) any_cat |= (sv.ft[e] == FEAT_CAT);  // CTA-uniform: all-numeric problems skip the bitmask test
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_d = *tmem_slot;
+    const int items = nt_n * PU_SLICES;
+    const int last_cols = kt_n * PU_KB - (nt_n - 1) * PU_N;  // columns of the last column tile (128 or 256)
 
-    if (warp == 5) {
+    if (warp == 1) {
+        // ================= producer: digit tiles of sample after sample, items in order, K tiles kt >= pu_kt_lo(nt)
         if (lane == 0) {
-            for (int ld = nstages; ld < loads; ++ld) {
-                const int s = ld % nstages;
-                const int nt = ld / (PU_SLICES * kt_n);
-                const uint32_t bytes = (uint32_t)((nt == nt_n - 1) ? last_cols : PU_N) * PU_KB;
-                pu_mbar_wait(empty_bar + s, (uint32_t)((ld / nstages - 1) & 1), pu_status);
-                pu_mbar_expect_tx(full_bar + s, bytes);
-                pu_bulk_g2s(ring + (size_t)s * PU_B_TILE, src_tiles + (size_t)ld * PU_B_TILE, bytes, full_bar + s);
-            }
-        }
-        __syncwarp();
-    } else if (warp == 4) {
-        if (lane == 0) {
-            // ---- MMA issuer: item = (column tile, digit plane) into TMEM buffer item & 1
             int ld = 0;
-            for (int it = 0; it < items; ++it) {
-                const int nt = it / PU_SLICES, buf = it & 1, use = it >> 1;
-                const int ncols = (nt == nt_n - 1) ? last_cols : PU_N;
-                const uint32_t idesc = pu_idesc_i8(PU_ROWS, ncols);
-                if (use > 0) pu_mbar_wait(acc_free + buf, (uint32_t)((use - 1) & 1), pu_status);  // epilogue has drained the buffer
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                for (int kt = 0; kt < kt_n; ++kt, ++ld) {
-                    const int s = ld % nstages;
-                    pu_mbar_wait(full_bar + s, (uint32_t)((ld / nstages) & 1), pu_status);
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const uint32_t a_addr = pu_smem(a_tiles + (size_t)kt * PU_A_TILE);
-                    const uint32_t b_addr = pu_smem(ring + (size_t)s * PU_B_TILE);
-#pragma unroll
-                    for (int k4 = 0; k4 < PU_KB / 32; ++k4)
-                        pu_umma_i8(tmem_d + (uint32_t)(buf * PU_N), pu_desc_sw128(a_addr + k4 * 32),
-                                   pu_desc_sw128(b_addr + k4 * 32), idesc, (kt > 0 || k4 > 0) ? 1u : 0u);
-                    pu_commit(empty_bar + s);
-                }
-                pu_commit(acc_full + buf);
-            }
-        }
-        __syncwarp();
-    } else {
-        // ---- epilogue: masked int32 row sums of every digit plane.  A warp reads the TMEM lanes of its quarter
-        // (warp % 4), thread = candidate row; the four groups share the 32-column chunks of every item.
-        const int row = 32 * (warp & 3) + lane;
-        int acc[PU_SLICES];
-#pragma unroll
-        for (int s = 0; s < PU_SLICES; ++s) acc[s] = 0;
-        int it = 0;
-        for (int nt = 0; nt < nt_n; ++nt) {
-            const int ncols = (nt == nt_n - 1) ? last_cols : PU_N;
-            unsigned long long zm[PU_N / 64];
-#pragma unroll
-            for (int q = 0; q < PU_N / 64; ++q) zm[q] = (q * 64 < ncols) ? zmask[(size_t)(nt * (PU_N / 64) + q) * PU_ROWS + row] : 0ull;
-#pragma unroll
-            for (int s = 0; s < PU_SLICES; ++s, ++it) {
-                const int buf = it & 1, use = it >> 1;
-                pu_mbar_wait(acc_full + buf, (uint32_t)(use & 1), pu_status);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                int a = acc[s];
-#pragma unroll
-                for (int j = 0; j < PU_N / 32; ++j) {
-                    if ((j % PU_WALK_GROUPS) != wg) continue;  // warp-uniform
-                    const uint32_t bits = (uint32_t)(zm[j >> 1] >> (32 * (j & 1)));
-                    if (__any_sync(0xffffffffu, bits != 0u)) {
-                        uint32_t v[32];
-                        pu_tmem_ld32(tmem_d + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(buf * PU_N + 32 * j), v);
-#pragma unroll
-                        for (int c = 0; c < 32; ++c) a += (int)v[c] * (int)((bits >> c) & 1u);
+            for (int si = 0; si < ns; ++si) {
+                const int64_t sample = s_lo + si;
+                unsigned* st = &chain_view(lay, const_cast<void*>(ws), sample).sc->status;
+                const uint8_t* src_tiles = tiles + (size_t)sample * nt_n * PU_SLICES * kt_n * PU_B_TILE;
+                for (int it = 0; it < items; ++it) {
+                    const int nt = it / PU_SLICES;
+                    const uint32_t bytes = (uint32_t)((nt == nt_n - 1) ? last_cols : PU_N) * PU_KB;
+                    for (int kt = pu_kt_lo(nt); kt < kt_n; ++kt, ++ld) {
+                        const int s = ld % nstages;
+                        PU_T0();
+                        if (ld >= nstages) pu_mbar_wait(empty_bar + s, (uint32_t)((ld / nstages - 1) & 1), st);
+                        PU_ACC(0);
+                        pu_mbar_expect_tx(full_bar + s, bytes);
+                        pu_bulk_g2s(ring + (size_t)s * PU_B_TILE, src_tiles + ((size_t)it * kt_n + kt) * PU_B_TILE, bytes, full_bar + s);
+                        PU_ACC(1);
                     }
                 }
-                acc[s] = a;
-                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                pu_mbar_arrive(acc_free + buf);
             }
+            PU_REPORT("pu_producer per sample: wait_empty %lld issue %lld\n", pu_w[0] / ns, pu_w[1] / ns);
         }
-        if (wg > 0) {
+        __syncwarp();
+    } else if (warp == 0) {
+        // ================= MMA issuer: item = (column tile, digit plane) into TMEM buffer (running item index) & 1
+        if (lane == 0) {
+            int ld = 0, git = 0;
+            for (int si = 0; si < ns; ++si) {
+                unsigned* st = &chain_view(lay, const_cast<void*>(ws), s_lo + si).sc->status;
+                PU_T0();
+                pu_mbar_wait(a_ready, (uint32_t)(si & 1), st);  // A operand of this sample written (and proxy-fenced)
+                PU_ACC(0);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                for (int it = 0; it < items; ++it, ++git) {
+                    const int nt = it / PU_SLICES, buf = git & 1, use = git >> 1;
+                    const int ncols = (nt == nt_n - 1) ? last_cols : PU_N;
+                    const uint32_t idesc = pu_idesc_i8(PU_ROWS, ncols);
+                    PU_T0();
+                    if (use > 0) pu_mbar_wait(acc_free + buf, (uint32_t)((use - 1) & 1), st);  // epilogue has drained the buffer
+                    PU_ACC(1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const int kt_lo = pu_kt_lo(nt);
+                    for (int kt = kt_lo; kt < kt_n; ++kt, ++ld) {
+                        const int s = ld % nstages;
+                        PU_T0();
+                        pu_mbar_wait(full_bar + s, (uint32_t)((ld / nstages) & 1), st);
+                        PU_ACC(2);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        const uint32_t a_addr = pu_smem(a_tiles + (size_t)kt * PU_A_TILE);
+                        const uint32_t b_addr = pu_smem(ring + (size_t)s * PU_B_TILE);
 #pragma unroll
-            for (int s = 0; s < PU_SLICES; ++s) accp[((wg - 1) * PU_SLICES + s) * PU_ROWS + row] = acc[s];
-        }
-        asm volatile("bar.sync 1, %0;" ::"r"(PU_WALK_GROUPS * PU_ROWS) : "memory");  // the epilogue warps only
-        if (wg == 0 && row < np) {
-            // z^T Binv z = 2^-shift * sum_k 256^k acc_k   (each acc_k exact)
-            double tsum = 0.0;
-#pragma unroll
-            for (int s = PU_SLICES - 1; s >= 0; --s) {
-                int a = acc[s];
-#pragma unroll
-                for (int g = 1; g < PU_WALK_GROUPS; ++g) a += accp[((g - 1) * PU_SLICES + s) * PU_ROWS + row];
-                tsum = tsum * 256.0 + (double)a;
+                        for (int k4 = 0; k4 < PU_KB / 32; ++k4)
+                            pu_umma_i8(tmem_d + (uint32_t)(buf * PU_N), pu_desc_sw128(a_addr + k4 * 32),
+                                       pu_desc_sw128(b_addr + k4 * 32), idesc, (kt > kt_lo || k4 > 0) ? 1u : 0u);
+                        pu_commit(empty_bar + s);
+                        PU_ACC(3);
+                    }
+                    pu_commit(acc_full + buf);
+                }
             }
+            PU_REPORT("pu_mma per sample: wait_a_ready %lld wait_acc_free %lld wait_full %lld issue %lld\n", pu_w[0] / ns, pu_w[1] / ns, pu_w[2] / ns,
+                      pu_w[3] / ns);
+        }
+        __syncwarp();
+    } else if (warp >= PU_FIRST_WALK) {
+        // ================= walkers: PU_WALK_GROUPS threads per candidate, one sample ahead of the MMAs
+        const int wt = tid - PU_FIRST_WALK * 32;  // 0 .. 32 * PU_WALK_WARPS - 1
+        const int wg = wt / PU_ROWS, row = wt % PU_ROWS;
+        constexpr int WALKERS = 32 * PU_WALK_WARPS;
+        for (int si = 0; si < ns; ++si) {
+            const int64_t sample = s_lo + si;
+            const int par = si % nb, gen = si / nb;  // mask buffer and how often it has been used before
+            ChainView cv = chain_view(lay, const_cast<void*>(ws), sample);
+            unsigned long long* zm = zmask + (size_t)par * mask_words;
+            PU_T0();
+            if (gen > 0) pu_mbar_wait(mask_free + par, (uint32_t)((gen - 1) & 1), &cv.sc->status);
+            PU_ACC(0);
+            {
+                const WalkNode* src = table + (size_t)sample * m * hi;
+                for (int e = wt; e < m * hi; e += WALKERS) tb[e] = src[e];
+                for (int e = wt; e < kt_n * PU_KB; e += WALKERS) w_s[e] = (e < lay.P) ? cv.w[e] : 0.0;
+                for (int e = wt; e < mask_words; e += WALKERS) zm[e] = 0ull;
+            }
+            pu_named_sync(2, WALKERS);
+            PU_ACC(1);
             double mean = 0.0;
+            if (row < np) {
+                const double* xp = xs + row;
+                const float* xfp = xf + row;
+                unsigned* zm32 = reinterpret_cast<unsigned*>(zm);
+                // four trees in flight per thread, branch-free (a leaf steps to itself) so that the four pointer chases
+                // overlap; the partial mean keeps the order of t
+                for (int t0 = wg; t0 < m; t0 += 4 * PU_WALK_GROUPS) {
+                    WalkNode nd[4];
+                    const WalkNode* wn[4];
+                    uint32_t cur[4];
 #pragma unroll
-            for (int g = 0; g < PU_WALK_GROUPS; ++g) mean += meanp[g * PU_ROWS + row];
-            const int64_t o = sample * n_c + p0 + row;
-            mu[o] = mean;
-            var[o] = cv.sc->sig * (tsum * scales[sample]);
+                    for (int u = 0; u < 4; ++u) {
+                        wn[u] = tb + (size_t)min(t0 + u * PU_WALK_GROUPS, m - 1) * hi;
+                        nd[u] = wn[u][0];
+                        cur[u] = 0;
+                    }
+                    for (int it = 0; it < hi; ++it) {
+                        if ((nd[0].feat_leaf & nd[1].feat_leaf & nd[2].feat_leaf & nd[3].feat_leaf) & 0x8000u) break;
+                        float xv[4];
+                        int fi[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            fi[u] = min((int)(nd[u].feat_leaf & 0x7fffu), d - 1);  // (a leaf's feature bits are ignored below)
+                            xv[u] = xfp[(size_t)fi[u] * (PU_ROWS + 1)];
+                        }
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            bool left = xv[u] <= nd[u].thr;
+                            if (any_cat && ftc[fi[u]] == FEAT_CAT) left = goes_left(xp[(size_t)fi[u] * (PU_ROWS + 1)], nd[u].thr, FEAT_CAT);
+                            const uint32_t at = min((uint32_t)(left ? nd[u].left : nd[u].right), (uint32_t)(hi - 1));
+                            cur[u] = (nd[u].feat_leaf & 0x8000u) ? cur[u] : at;
+                        }
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) nd[u] = wn[u][cur[u]];
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        if (t0 + u * PU_WALK_GROUPS >= m) break;
+                        const int col = __float_as_int(nd[u].thr);
+                        mean += w_s[col];
+                        atomicOr(zm32 + 2 * ((size_t)(col >> 6) * PU_ROWS + row) + ((col >> 5) & 1), 1u << (col & 31));
+                    }
+                }
+            }
+            meanp[((size_t)par * PU_WALK_GROUPS + wg) * PU_ROWS + row] = mean;
+            pu_named_sync(2, WALKERS);  // every walker is done with the table / w of this sample (and its masks are written)
+            if (lane == 0) pu_mbar_arrive(mask_ready + par);
+            PU_ACC(2);
         }
+        if (wt == 0) PU_REPORT("pu_walker per sample: wait_mask_free %lld stage %lld walk %lld\n", pu_w[0] / ns, pu_w[1] / ns, pu_w[2] / ns);
+    } else {
+        // ================= epilogue warps: A operand of the next sample, masked int32 row sums of every digit plane
+        const int ew = warp - PU_FIRST_EPI;
+        const int quarter = warp & 3, half = ew >> 2;  // TMEM lane quarter of this warp; which 128 of an item's 256 columns
+        const int row = 32 * quarter + lane;
+        const int et = tid - PU_FIRST_EPI * 32;  // 0 .. 255
+        constexpr int EPI = 32 * PU_EPI_WARPS;
+        const bool narrow = (m * 128 <= 32767);  // |T_k| <= 128 m fits int16
+
+        auto build_a = [&](int si) {
+            // one-hot A operand (K-major, SWIZZLE_128B) from the masks of sample si: one 16-byte chunk per thread and step
+            unsigned* st = &chain_view(lay, const_cast<void*>(ws), s_lo + si).sc->status;
+            PU_T0();
+            pu_mbar_wait(mask_ready + si % nb, (uint32_t)((si / nb) & 1), st);
+            PU_ACC(0);
+            const unsigned long long* zm = zmask + (size_t)(si % nb) * mask_words;
+            const int chunks_per_row = kt_n * 8;
+            for (int e = et; e < PU_ROWS * chunks_per_row; e += EPI) {
+                const int r_ = e % PU_ROWS, ch = e / PU_ROWS;  // rows fastest: consecutive mask words, 8 swizzled chunks per group
+                const uint32_t bits = (uint32_t)(zm[(size_t)(ch >> 2) * PU_ROWS + r_] >> ((ch & 3) * 16)) & 0xFFFFu;
+                const uint32_t r = (uint32_t)r_, c = (uint32_t)(ch & 7);
+                unsigned char* dst = a_tiles + (size_t)(ch >> 3) * PU_A_TILE + (r >> 3) * 1024u + (r & 7) * 128u + ((c ^ (r & 7)) << 4);
+                *reinterpret_cast<uint4*>(dst) = pu_expand16(bits);
+            }
+            asm volatile("fence.proxy.async;" ::: "memory");  // generic writes of the A operand -> tensor-core (async proxy) reads
+            __syncwarp();
+            if (lane == 0) pu_mbar_arrive(a_ready);
+            PU_ACC(1);
+        };
+
+        if (ns > 0) build_a(0);
+        int git = 0;
+        for (int si = 0; si < ns; ++si) {
+            const int64_t sample = s_lo + si;
+            const int par = si % nb;
+            ChainView cv = chain_view(lay, const_cast<void*>(ws), sample);
+            unsigned* st = &cv.sc->status;
+            const unsigned long long* zm = zmask + (size_t)par * mask_words;
+            int acc[PU_SLICES];
+#pragma unroll
+            for (int s = 0; s < PU_SLICES; ++s) acc[s] = 0;
+            for (int nt = 0; nt < nt_n; ++nt) {
+                const int ncols = (nt == nt_n - 1) ? last_cols : PU_N;
+                // this warp's 128 columns of the item = two 64-column mask words of its row
+                const int w0 = nt * (PU_N / 64) + 2 * half;
+                const unsigned long long bits0 = (half * 128 < ncols) ? zm[(size_t)w0 * PU_ROWS + row] : 0ull;
+                const unsigned long long bits1 = (half * 128 + 64 < ncols) ? zm[(size_t)(w0 + 1) * PU_ROWS + row] : 0ull;
+#pragma unroll
+                for (int s = 0; s < PU_SLICES; ++s, ++git) {
+                    const int buf = git & 1, use = git >> 1;
+                    PU_T0();
+                    pu_mbar_wait(acc_full + buf, (uint32_t)(use & 1), st);
+                    PU_ACC(2);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t taddr = tmem_d + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * PU_N + 128 * half);
+                    int a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+                    if (__any_sync(0xffffffffu, (bits0 | bits1) != 0ull)) {
+                        if (narrow) {
+                            // packed loads (two int16 columns per register), both issued before the single wait; one dp2a
+                            // per register against the row's 0 / 1 mask bytes
+                            uint32_t v0[32], v1[32];
+                            pu_tmem_ld64_pack16(taddr, v0);
+                            pu_tmem_ld64_pack16(taddr + 64, v1);
+                            pu_tmem_wait_ld();
+#pragma unroll
+                            for (int r = 0; r < 16; ++r) {
+                                const uint32_t m0 = (((uint32_t)(bits0 >> (4 * r)) & 0xFu) * 0x00204081u) & 0x01010101u;
+                                const uint32_t m1 = (((uint32_t)(bits1 >> (4 * r)) & 0xFu) * 0x00204081u) & 0x01010101u;
+                                a0 = __dp2a_lo((int)v0[2 * r], (int)m0, a0);
+                                a1 = __dp2a_hi((int)v0[2 * r + 1], (int)m0, a1);
+                                a2 = __dp2a_lo((int)v1[2 * r], (int)m1, a2);
+                                a3 = __dp2a_hi((int)v1[2 * r + 1], (int)m1, a3);
+                            }
+                        } else {
+#pragma unroll 1
+                            for (int j = 0; j < 4; ++j) {
+                                uint32_t v[32];
+                                pu_tmem_ld32(taddr + 32 * j, v);
+                                pu_tmem_wait_ld();
+                                const uint32_t b = (uint32_t)((j < 2 ? bits0 : bits1) >> (32 * (j & 1)));
+#pragma unroll
+                                for (int c = 0; c < 32; ++c) a0 += (int)v[c] * (int)((b >> c) & 1u);
+                            }
+                        }
+                    }
+                    acc[s] += (a0 + a1) + (a2 + a3);
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) pu_mbar_arrive(acc_free + buf);
+                    PU_ACC(3);
+                }
+            }
+            PU_T0();
+            // every MMA of this sample has completed (the last acc_full): the A operand may be rewritten.  (With a single
+            // mask buffer the next sample's masks only appear after this sample's are released: build A at the end.)
+            if (nb > 1 && si + 1 < ns) build_a(si + 1);
+            if (half == 1) {
+#pragma unroll
+                for (int s = 0; s < PU_SLICES; ++s) accp[s * PU_ROWS + row] = acc[s];
+            }
+            pu_named_sync(1, EPI);
+            if (half == 0 && row < np) {
+                // z^T Binv z = 2^-shift * sum_k 256^k acc_k   (each acc_k exact)
+                double tsum = 0.0;
+#pragma unroll
+                for (int s = PU_SLICES - 1; s >= 0; --s) tsum = tsum * 256.0 + (double)(acc[s] + accp[s * PU_ROWS + row]);
+                double mean = 0.0;
+#pragma unroll
+                for (int g = 0; g < PU_WALK_GROUPS; ++g) mean += meanp[((size_t)par * PU_WALK_GROUPS + g) * PU_ROWS + row];
+                const int64_t o = sample * n_c + p0 + row;
+                mu[o] = mean;
+                var[o] = cv.sc->sig * (tsum * scales[sample]);
+            }
+            pu_named_sync(1, EPI);  // accp / meanp / masks of this sample are no longer needed
+            if (lane == 0) pu_mbar_arrive(mask_free + par);
+            PU_ACC(4);
+            if (nb == 1 && si + 1 < ns) build_a(si + 1);
+        }
+        if (et == 0) PU_REPORT("pu_epilogue per sample: wait_mask_ready %lld build_a %lld wait_acc_full %lld drain %lld output %lld\n", pu_w[0] / ns,
+                               pu_w[1] / ns, pu_w[2] / ns, pu_w[3] / ns, pu_w[4] / ns);
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 4) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(512u) : "memory");
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(512u) : "memory");
 }
 
 }  // namespace bark
@@ -453,16 +645,25 @@ int bark_predict_umma(const bark_mcmc_dims* dims, const void* workspace, const v
     const WsLayout lay = make_layout(*dims);
     const PrepLayout pl = prep_layout(dims->chains, dims->m, slots, p_max);
     const int stage_bytes = PU_B_TILE;
-    const size_t fixed = pu_smem_layout((int)lay.m, slots, (int)lay.d, pl.kt, 0).total;
+    // two mask buffers (the walk runs a sample ahead of the MMAs) when they fit beside a ring of >= 2 stages, else one
+    int nb = 2;
+    size_t fixed = pu_smem_layout((int)lay.m, slots, (int)lay.d, pl.kt, 0, nb).total;
+    if (fixed + 2 * (size_t)stage_bytes > 227 * 1024) {
+        nb = 1;
+        fixed = pu_smem_layout((int)lay.m, slots, (int)lay.d, pl.kt, 0, nb).total;
+    }
     BARK_CHECK_ARG(fixed + 2 * (size_t)stage_bytes <= 227 * 1024, "m * slots / d / p_max too large for the predict kernel's shared memory");
     const int ring_bytes = (int)(std::min<size_t>(PU_RING_MAX, 227 * 1024 - fixed) / stage_bytes) * stage_bytes;
-    const PuSmem sl = pu_smem_layout((int)lay.m, slots, (int)lay.d, pl.kt, ring_bytes);
+    const PuSmem sl = pu_smem_layout((int)lay.m, slots, (int)lay.d, pl.kt, ring_bytes, nb);
     BARK_CUDA(cudaFuncSetAttribute(predict_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sl.total));
     const unsigned char* base = (const unsigned char*)prep;
-    dim3 grid((unsigned)ceil_div(n_c, PU_ROWS), (unsigned)dims->chains);
+    // one persistent CTA per candidate tile loops over the samples; with fewer tiles than SMs the samples are split
+    const int64_t tiles_n = ceil_div(n_c, PU_ROWS);
+    const int64_t ysplit = std::max<int64_t>(1, std::min<int64_t>(dims->chains, 148 / tiles_n));
+    dim3 grid((unsigned)tiles_n, (unsigned)ysplit);
     predict_umma_kernel<<<grid, PU_THREADS, sl.total, (cudaStream_t)stream>>>(
         lay, workspace, (const WalkNode*)(base + pl.off_table), base + pl.off_tiles, (const double*)(base + pl.off_scale),
-        slots, pl.kt, pl.nt, ring_bytes, candidates, n_c, mu, var);
+        slots, pl.kt, pl.nt, ring_bytes, nb, candidates, n_c, mu, var);
     BARK_LAUNCH_CHECK();
     return BARK_OK;
 }

@@ -42,7 +42,7 @@ class PosteriorState:
         self.slots = forest_slots(forest)
         self.p_max = int(st.read()["p_used"].max().item())
         self.prep = None
-        self.k_pad = None  # one-hot width of the int8 GEMM (multiple of 128): 2 * 7 * k_pad^2 int8 ops per candidate-sample
+        self.k_pad = None  # one-hot width of the int8 GEMM (multiple of 128); see umma_ops_per_candidate_sample
         # (extents above 768 columns, or tensor_cores=False, use the FP64 gather kernel of csrc/predict.cu)
         nbytes = int(st.lib.bark_predict_prep_bytes(C.byref(st.dims), self.slots, self.p_max)) if (tensor_cores and self.p_max <= 768) else 0
         if nbytes:
@@ -51,6 +51,21 @@ class PosteriorState:
             self.k_pad = ((self.p_max + 127) // 128) * 128
             _lib.check(st.lib.bark_predict_prepare(C.byref(st.dims), _ptr(st.ws), st.dforest.soa(), self.slots, self.p_max,
                                                    _ptr(self.prep), _stream()))
+
+    @property
+    def umma_ops_per_candidate_sample(self):
+        """int8 multiply-adds x 2 that the tensor-core path executes per (candidate, posterior sample): 7 digit planes of
+        the triangular operand -- column tiles of 256 (the last may be 128), K tiles of 128 from the diagonal down
+        (csrc/predict_umma.cu, pu_kt_lo)."""
+        if not self.k_pad:
+            return None
+        kt = self.k_pad // 128
+        ops, nt = 0, 0
+        while nt * 256 < self.k_pad:
+            ncols = min(256, self.k_pad - nt * 256)
+            ops += 2 * 7 * ncols * 128 * (kt - 2 * nt)
+            nt += 1
+        return ops
 
     def check(self):
         raise_for_status(self.state.read()["status"].cpu().numpy())

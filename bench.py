@@ -455,10 +455,10 @@ def predict_measure(D, model, data, n_c, pk, ncu, steps=3, warmup=1, with_e2e=Tr
     out = {"points_per_s": value, "candidate_samples_per_s": value * S, "n_candidates_per_gpu": n_c, "posterior_samples": S,
            "ms_per_step": ms_step, "algorithmic_hbm_bytes_per_point": 8 * d + 16,
            "hbm_gbs": value / D.world * (8 * d + 16) / 1e9}
-    # int8 UMMA work issued per candidate-sample: 7 digit planes x (one-hot row of K_pad columns) x N_pad outputs
+    # int8 UMMA work executed per candidate-sample: 7 digit planes x (one-hot row) x the triangular operand's tiles
     kp = getattr(ps, "k_pad", None)
     if kp:
-        ops = 2.0 * kp * kp * 7
+        ops = float(ps.umma_ops_per_candidate_sample)
         tops = value / D.world * S * ops / 1e12
         out["roofline"] = {"kernel": "predict_umma_kernel", "bound": "tensor", "pipe": "int8 tcgen05 (kind::i8)", "achieved": tops,
                            "peak": pk["int8_tops"], "unit": "TOP/s", "frac": tops / pk["int8_tops"],
