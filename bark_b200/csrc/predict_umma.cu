@@ -270,7 +270,7 @@ __global__ void __launch_bounds__(PU_THREADS, 1)
 predict_umma_kernel(WsLayout lay, const void* ws, const WalkNode* __restrict__ table, const uint8_t* __restrict__ tiles,
                     const double* __restrict__ scales, int hi, int kt_n, int nt_n, int ring_bytes, int nb,
                     const double* __restrict__ cand,
-                    int64_t n_c, double* __restrict__ mu, double* __restrict__ var) {
+                    int64_t n_c, double* __restrict__ mu, double* __restrict__ var, int pu_exp) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     const int d = (int)lay.d, m = (int)lay.m;
     const PuSmem sl = pu_smem_layout(m, hi, d, kt_n, ring_bytes, nb);  // nb = 2: the walk runs one sample ahead; 1: tight shared memory
@@ -299,6 +299,11 @@ predict_umma_kernel(WsLayout lay, const void* ws, const WalkNode* __restrict__ t
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 #ifdef BARK_PHASE_TIMING
     long long pu_w[6] = {0, 0, 0, 0, 0, 0}, pu_c = 0;
+    __shared__ long long pu_tl[6][16];  // timeline of sample 20: [event][item]
+    const bool pu_trace = (blockIdx.x == gridDim.x / 2 && blockIdx.y == 0);
+#define PU_TL(ev, si_, it_) do { if (pu_trace && (si_) == 20 && (it_) < 16) pu_tl[ev][it_] = clock64(); } while (0)
+#else
+#define PU_TL(ev, si_, it_) do { } while (0)
 #endif
     const int64_t p0 = (int64_t)blockIdx.x * PU_ROWS;
     const int np = (int)min((int64_t)PU_ROWS, n_c - p0);
@@ -340,27 +345,40 @@ predict_umma_kernel(WsLayout lay, const void* ws, const WalkNode* __restrict__ t
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_d = *tmem_slot;
     const int items = nt_n * PU_SLICES;
+    (void)items;
     const int last_cols = kt_n * PU_KB - (nt_n - 1) * PU_N;  // columns of the last column tile (128 or 256)
 
     if (warp == 1) {
-        // ================= producer: digit tiles of sample after sample, items in order, K tiles kt >= pu_kt_lo(nt)
+        // ================= producer: digit tiles of sample after sample, items in order, K tiles kt >= pu_kt_lo(nt).
+        // (Both single-thread loops below keep their bookkeeping incremental -- ring position and phase, source pointer,
+        // descriptors by addition: one lone thread runs ~5 cycles per dependent instruction, and an integer division by
+        // the runtime stage count per tile was costing more than the tile's four MMAs.)
         if (lane == 0) {
-            int ld = 0;
+            int stage = 0;
+            uint32_t phase = 1;  // parity of the empty-barrier phase that must have completed: first lap needs none
+            bool first_lap = true;
             for (int si = 0; si < ns; ++si) {
                 const int64_t sample = s_lo + si;
                 unsigned* st = &chain_view(lay, const_cast<void*>(ws), sample).sc->status;
-                const uint8_t* src_tiles = tiles + (size_t)sample * nt_n * PU_SLICES * kt_n * PU_B_TILE;
-                for (int it = 0; it < items; ++it) {
-                    const int nt = it / PU_SLICES;
+                const uint8_t* src_item = tiles + (size_t)sample * nt_n * PU_SLICES * kt_n * PU_B_TILE;
+                for (int nt = 0; nt < nt_n; ++nt) {
                     const uint32_t bytes = (uint32_t)((nt == nt_n - 1) ? last_cols : PU_N) * PU_KB;
-                    for (int kt = pu_kt_lo(nt); kt < kt_n; ++kt, ++ld) {
-                        const int s = ld % nstages;
-                        PU_T0();
-                        if (ld >= nstages) pu_mbar_wait(empty_bar + s, (uint32_t)((ld / nstages - 1) & 1), st);
-                        PU_ACC(0);
-                        pu_mbar_expect_tx(full_bar + s, bytes);
-                        pu_bulk_g2s(ring + (size_t)s * PU_B_TILE, src_tiles + ((size_t)it * kt_n + kt) * PU_B_TILE, bytes, full_bar + s);
-                        PU_ACC(1);
+                    const int kt_lo = pu_kt_lo(nt);
+                    for (int sl_ = 0; sl_ < PU_SLICES; ++sl_, src_item += (size_t)kt_n * PU_B_TILE) {
+                        const uint8_t* src = src_item + (size_t)kt_lo * PU_B_TILE;
+                        for (int kt = kt_lo; kt < kt_n; ++kt, src += PU_B_TILE) {
+                            PU_T0();
+                            if (!first_lap) pu_mbar_wait(empty_bar + stage, phase, st);
+                            PU_ACC(0);
+                            pu_mbar_expect_tx(full_bar + stage, bytes);
+                            pu_bulk_g2s(ring + (size_t)stage * PU_B_TILE, src, bytes, full_bar + stage);
+                            PU_ACC(1);
+                            if (++stage == nstages) {
+                                stage = 0;
+                                phase ^= first_lap ? 0u : 1u;
+                                if (first_lap) { first_lap = false; phase = 0; }
+                            }
+                        }
                     }
                 }
             }
@@ -370,38 +388,49 @@ predict_umma_kernel(WsLayout lay, const void* ws, const WalkNode* __restrict__ t
     } else if (warp == 0) {
         // ================= MMA issuer: item = (column tile, digit plane) into TMEM buffer (running item index) & 1
         if (lane == 0) {
-            int ld = 0, git = 0;
+            int stage = 0;
+            uint32_t full_phase = 0;
+            uint32_t git = 0;  // running item index: TMEM buffer git & 1, its use count git >> 1
+            const uint64_t desc_hi = (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);  // pu_desc_sw128 without the address
+            const uint64_t a_desc0 = desc_hi | (uint64_t)((pu_smem(a_tiles) >> 4) & 0x3FFFu);
+            const uint64_t b_desc0 = desc_hi | (uint64_t)((pu_smem(ring) >> 4) & 0x3FFFu);
+            const uint32_t idesc_full = pu_idesc_i8(PU_ROWS, PU_N), idesc_last = pu_idesc_i8(PU_ROWS, last_cols);
             for (int si = 0; si < ns; ++si) {
                 unsigned* st = &chain_view(lay, const_cast<void*>(ws), s_lo + si).sc->status;
                 PU_T0();
                 pu_mbar_wait(a_ready, (uint32_t)(si & 1), st);  // A operand of this sample written (and proxy-fenced)
                 PU_ACC(0);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                for (int it = 0; it < items; ++it, ++git) {
-                    const int nt = it / PU_SLICES, buf = git & 1, use = git >> 1;
-                    const int ncols = (nt == nt_n - 1) ? last_cols : PU_N;
-                    const uint32_t idesc = pu_idesc_i8(PU_ROWS, ncols);
-                    PU_T0();
-                    if (use > 0) pu_mbar_wait(acc_free + buf, (uint32_t)((use - 1) & 1), st);  // epilogue has drained the buffer
-                    PU_ACC(1);
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                for (int nt = 0; nt < nt_n; ++nt) {
+                    const uint32_t idesc = (nt == nt_n - 1) ? idesc_last : idesc_full;
                     const int kt_lo = pu_kt_lo(nt);
-                    for (int kt = kt_lo; kt < kt_n; ++kt, ++ld) {
-                        const int s = ld % nstages;
+                    for (int sl_ = 0; sl_ < PU_SLICES; ++sl_) {
+                        const uint32_t buf = git & 1u, use = git >> 1;
                         PU_T0();
-                        pu_mbar_wait(full_bar + s, (uint32_t)((ld / nstages) & 1), st);
-                        PU_ACC(2);
+                        if (use > 0) pu_mbar_wait(acc_free + buf, (use - 1) & 1u, st);  // epilogue has drained the buffer
+                        PU_ACC(1);
+                        PU_TL(0, si, nt * PU_SLICES + sl_);
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                        const uint32_t a_addr = pu_smem(a_tiles + (size_t)kt * PU_A_TILE);
-                        const uint32_t b_addr = pu_smem(ring + (size_t)s * PU_B_TILE);
-#pragma unroll
-                        for (int k4 = 0; k4 < PU_KB / 32; ++k4)
-                            pu_umma_i8(tmem_d + (uint32_t)(buf * PU_N), pu_desc_sw128(a_addr + k4 * 32),
-                                       pu_desc_sw128(b_addr + k4 * 32), idesc, (kt > kt_lo || k4 > 0) ? 1u : 0u);
-                        pu_commit(empty_bar + s);
-                        PU_ACC(3);
+                        const uint32_t d_addr = tmem_d + buf * PU_N;
+                        uint64_t a_desc = a_desc0 + (uint64_t)(kt_lo * (PU_A_TILE >> 4));
+                        for (int kt = kt_lo; kt < kt_n; ++kt, a_desc += (PU_A_TILE >> 4)) {
+                            PU_T0();
+                            pu_mbar_wait(full_bar + stage, full_phase, st);
+                            PU_ACC(2);
+                            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                            const uint64_t b_desc = b_desc0 + (uint64_t)(stage * (PU_B_TILE >> 4));
+                            pu_umma_i8(d_addr, a_desc, b_desc, idesc, kt > kt_lo ? 1u : 0u);
+                            pu_umma_i8(d_addr, a_desc + 2, b_desc + 2, idesc, 1u);
+                            pu_umma_i8(d_addr, a_desc + 4, b_desc + 4, idesc, 1u);
+                            pu_umma_i8(d_addr, a_desc + 6, b_desc + 6, idesc, 1u);
+                            pu_commit(empty_bar + stage);
+                            PU_ACC(3);
+                            if (++stage == nstages) { stage = 0; full_phase ^= 1u; }
+                        }
+                        pu_commit(acc_full + buf);
+                        PU_TL(1, si, nt * PU_SLICES + sl_);
+                        ++git;
                     }
-                    pu_commit(acc_full + buf);
                 }
             }
             PU_REPORT("pu_mma per sample: wait_a_ready %lld wait_acc_free %lld wait_full %lld issue %lld\n", pu_w[0] / ns, pu_w[1] / ns, pu_w[2] / ns,
@@ -430,7 +459,7 @@ predict_umma_kernel(WsLayout lay, const void* ws, const WalkNode* __restrict__ t
             pu_named_sync(2, WALKERS);
             PU_ACC(1);
             double mean = 0.0;
-            if (row < np) {
+            if (row < np && !(pu_exp & 1)) {
                 const double* xp = xs + row;
                 const float* xfp = xf + row;
                 unsigned* zm32 = reinterpret_cast<unsigned*>(zm);
@@ -533,10 +562,11 @@ predict_umma_kernel(WsLayout lay, const void* ws, const WalkNode* __restrict__ t
                     PU_T0();
                     pu_mbar_wait(acc_full + buf, (uint32_t)(use & 1), st);
                     PU_ACC(2);
+                    if (et == 0) PU_TL(2, si, nt * PU_SLICES + s);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t taddr = tmem_d + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * PU_N + 128 * half);
                     int a0 = 0, a1 = 0, a2 = 0, a3 = 0;
-                    if (__any_sync(0xffffffffu, (bits0 | bits1) != 0ull)) {
+                    if (__any_sync(0xffffffffu, (bits0 | bits1) != 0ull) || (pu_exp & 2)) {
                         if (narrow) {
                             // packed loads (two int16 columns per register), both issued before the single wait; one dp2a
                             // per register against the row's 0 / 1 mask bytes
@@ -544,6 +574,7 @@ predict_umma_kernel(WsLayout lay, const void* ws, const WalkNode* __restrict__ t
                             pu_tmem_ld64_pack16(taddr, v0);
                             pu_tmem_ld64_pack16(taddr + 64, v1);
                             pu_tmem_wait_ld();
+                            if (et == 0) PU_TL(3, si, nt * PU_SLICES + s);
 #pragma unroll
                             for (int r = 0; r < 16; ++r) {
                                 const uint32_t m0 = (((uint32_t)(bits0 >> (4 * r)) & 0xFu) * 0x00204081u) & 0x01010101u;
@@ -569,6 +600,7 @@ predict_umma_kernel(WsLayout lay, const void* ws, const WalkNode* __restrict__ t
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                     __syncwarp();
                     if (lane == 0) pu_mbar_arrive(acc_free + buf);
+                    if (et == 0) PU_TL(4, si, nt * PU_SLICES + s);
                     PU_ACC(3);
                 }
             }
@@ -604,6 +636,13 @@ predict_umma_kernel(WsLayout lay, const void* ws, const WalkNode* __restrict__ t
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(512u) : "memory");
+#ifdef BARK_PHASE_TIMING
+    if (pu_trace && tid == 0 && ns > 20)
+        for (int it = 0; it < items && it < 16; ++it)
+            printf("pu_tl item %2d: mma_start %6lld mma_issued %6lld | acc_full_seen %6lld loads_done %6lld arrived %6lld\n", it,
+                   pu_tl[0][it] - pu_tl[0][0], pu_tl[1][it] - pu_tl[0][0], pu_tl[2][it] - pu_tl[0][0], pu_tl[3][it] - pu_tl[0][0],
+                   pu_tl[4][it] - pu_tl[0][0]);
+#endif
 }
 
 }  // namespace bark
@@ -663,7 +702,7 @@ int bark_predict_umma(const bark_mcmc_dims* dims, const void* workspace, const v
     dim3 grid((unsigned)tiles_n, (unsigned)ysplit);
     predict_umma_kernel<<<grid, PU_THREADS, sl.total, (cudaStream_t)stream>>>(
         lay, workspace, (const WalkNode*)(base + pl.off_table), base + pl.off_tiles, (const double*)(base + pl.off_scale),
-        slots, pl.kt, pl.nt, ring_bytes, nb, candidates, n_c, mu, var);
+        slots, pl.kt, pl.nt, ring_bytes, nb, candidates, n_c, mu, var, getenv("BARK_PU_EXP") ? atoi(getenv("BARK_PU_EXP")) : 0);
     BARK_LAUNCH_CHECK();
     return BARK_OK;
 }

@@ -87,6 +87,76 @@ __global__ void __launch_bounds__(128, 1) k(int iters, int group, long long* out
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(512u) : "memory");
 }
 
+// Fresh operands: B rotates through 4 x 32 KB stages and A through 4 tiles (no operand-collector reuse), and the
+// accumulator alternates between NACC TMEM buffers (consecutive MMAs into one accumulator form a dependent chain).
+template <bool TS, int N, int NACC>
+__global__ void __launch_bounds__(128, 1) k_rot(int iters, long long* out, int commit_every = 0) {
+    extern __shared__ __align__(1024) unsigned char sm[];  // A: 4 x 16 KB, B: 4 x 32 KB
+    __shared__ uint64_t bar, bar2;
+    __shared__ uint32_t tmem_slot;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int i = tid; i < (4 * 16384 + 4 * 32768) / 4; i += 128) reinterpret_cast<uint32_t*>(sm)[i] = 0x01010101u;
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&bar)), "r"(1) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&bar2)), "r"(1) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_d = tmem_slot;
+    if (TS) {
+        uint32_t v = 0x01010101u;
+        for (int c = 0; c < 128; ++c)
+            asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(tmem_d + ((uint32_t)(warp * 32) << 16) + c), "r"(v) : "memory");
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if (tid == 0) {
+        const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | (((uint32_t)N >> 3) << 17) | ((128u >> 4) << 24);
+        const uint32_t a_base = smem_u32(sm), b_base = a_base + 4 * 16384;
+        const long long t0 = clock64();
+        for (int it = 0; it < iters; ++it) {
+            const int k4 = it & 3, stage = (it >> 2) & 3, accb = it % NACC;
+            const uint32_t dcol = tmem_d + 128 + (uint32_t)(accb * N);
+            const uint32_t acc = (it >= NACC) ? 1u : 0u;
+            if (TS) mma_ts(dcol, tmem_d + stage * 32 + k4 * 8, desc_sw128(b_base + stage * 32768 + k4 * 32), idesc, acc);
+            else mma_ss(dcol, desc_sw128(a_base + stage * 16384 + k4 * 32), desc_sw128(b_base + stage * 32768 + k4 * 32), idesc, acc);
+            // a commit nobody waits for (the ring-slot release of a pipelined kernel): does it slow the MMA stream?
+            if (commit_every > 0 && ((it + 1) & (commit_every - 1)) == 0)
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar2)) : "memory");
+        }
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
+        wait_bar(&bar, 0);
+        const long long t1 = clock64();
+        if (blockIdx.x == 0) out[0] = t1 - t0;
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(512u) : "memory");
+}
+
+template <bool TS, int N, int NACC>
+static void run_rot(const char* name, long long* d, int commit_every = 0) {
+    const int iters = 4096, smem = 4 * 16384 + 4 * 32768 + 1024;
+    cudaFuncSetAttribute(k_rot<TS, N, NACC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    k_rot<TS, N, NACC><<<148, 128, smem>>>(iters, d, commit_every);
+    cudaDeviceSynchronize();
+    k_rot<TS, N, NACC><<<148, 128, smem>>>(iters, d, commit_every);
+    cudaError_t e = cudaDeviceSynchronize();
+    long long c = 0;
+    cudaMemcpy(&c, d, 8, cudaMemcpyDeviceToHost);
+    printf("{\"variant\": \"%s, rotating operands\", \"commit_every\": %d, \"N\": %d, \"accumulators\": %d, \"cycles_per_mma\": %.1f, \"int8_tops_148sm_1965mhz\": %.0f, \"cuda\": \"%s\"}\n",
+           name, commit_every, N, NACC, (double)c / iters, 2.0 * 128 * N * 32 / ((double)c / iters) * 148 * 1.965e9 / 1e12, cudaGetErrorString(e));
+}
+
 // TMEM read throughput: W warps (W % 4 == 0: every lane quarter gets W / 4 warps) read 32 lanes x 64 columns per step
 // (two 32x32b.x32 loads, one wait), optionally while thread 0 of an extra warp keeps the tensor pipe busy with N = 256 MMAs
 // into the other half of TMEM.
@@ -185,6 +255,19 @@ int main() {
     run<true, 128>("TS, commit + wait every 4", 4, d);
     run<false, 256>("SS, commit + wait every 16", 16, d);
     run<false, 256>("SS, commit + wait every 4", 4, d);
+    run_rot<false, 256, 1>("SS", d);
+    run_rot<false, 256, 1>("SS", d, 4);
+    run_rot<false, 256, 1>("SS", d, 8);
+    run_rot<false, 256, 1>("SS", d, 16);
+    run_rot<false, 128, 1>("SS", d, 4);
+    run_rot<true, 256, 1>("TS", d);
+    run_rot<false, 128, 1>("SS", d);
+    run_rot<false, 128, 2>("SS", d);
+    run_rot<true, 128, 1>("TS", d);
+    run_rot<true, 128, 2>("TS", d);
+    run_rot<true, 128, 3>("TS", d);
+    run_rot<true, 64, 4>("TS", d);
+    run_rot<true, 192, 2>("TS", d);
     for (int warps : {4, 8, 16})
         for (int with_mma : {0, 1}) run_ldtm(warps, with_mma, d);
     return 0;

@@ -375,6 +375,30 @@ def test_gram_umma_tensor_core_counts(n, n2, m):
     assert np.array_equal(K2.cpu().numpy(), wantK)
 
 
+@pytest.mark.parametrize("n,n2,m,slots", [(200, 130, 64, 40), (129, 129, 7, 256), (33, 500, 300, 3)])
+def test_gram_umma_wide_leaf_alphabets(n, n2, m, slots):
+    """Leaf ids drawn directly from [0, slots): more occupied (tree, slot) columns than one pass of the operand build
+    holds (20 K tiles at m = 64, slots = 40), presence masks of 1..8 words per tree, ragged tiles; counts stay exact, and an
+    id >= slots is refused."""
+    import torch
+    from bark_b200.forest import gram_umma_device
+    rng = np.random.default_rng(slots)
+    la = rng.integers(0, slots, size=(2, n, m), dtype=np.int64)
+    lb = rng.integers(0, slots, size=(2, n2, m), dtype=np.int64)
+    want = (la[:, :, None, :] == lb[:, None, :, :]).sum(-1).astype(np.int32)
+    dev = torch.device("cuda")
+    ta = torch.tensor(la.astype(np.int32), device=dev)
+    tb = torch.tensor(lb.astype(np.int32), device=dev)
+    cnt, _ = gram_umma_device(ta, tb, slots=slots)
+    assert np.array_equal(cnt.cpu().numpy(), want)
+    cnt2, _ = gram_umma_device(ta, ta, slots=slots)
+    assert np.array_equal(cnt2.cpu().numpy(), (la[:, :, None, :] == la[:, None, :, :]).sum(-1).astype(np.int32))
+    bad = ta.clone()
+    bad[1, n // 2, m // 2] = slots
+    with pytest.raises(B.BarkError):
+        gram_umma_device(bad, tb, slots=slots)
+
+
 def test_predict_both_paths_and_edges():
     """tcgen05 int8-sliced variance and the FP64 gather kernel agree with the oracle; ragged / empty candidate sets."""
     import torch
