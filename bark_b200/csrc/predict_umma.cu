@@ -5,18 +5,20 @@
 // (|Binv| <= 1/c bounds the scale) of the triangle { diag, 2 x strictly lower }:  z^T Binv z = 2^-shift * sum_k 256^k z^T D_k z.
 //
 // One persistent CTA per tile of 128 candidates loops over the posterior samples; its warps have fixed roles that run
-// concurrently, one sample apart:
-//   walkers (12 warps)   stage the sample's trees, walk them with three threads per candidate (four trees in flight per
-//                        thread), leaf columns -> the row's bit mask, partial means on the way;
-//   epilogue (8 warps)   expand the masks into the one-hot int8 A operand (K-major, SWIZZLE_128B) once the previous
-//                        sample's MMAs are done; drain the accumulators: z^T D_k z is the masked row sum of T_k = Z D_k,
-//                        read as packed int16 pairs (tcgen05.ld .pack::16b) and reduced with dp2a against the mask bytes;
-//   MMA issuer (1 thread) tcgen05.mma kind::i8, M = 128, N = 256 (N = 128 runs at half rate: scripts/umma_shapes.cu), one
-//                        (column tile, digit plane) item at a time into one of two 256-column TMEM accumulators, only
-//                        the K tiles on or below the diagonal band;
-//   producer (1 thread)  streams the digit tiles with the bulk-copy engine through a shared-memory ring, free-running
-//                        across samples.
+// concurrently, one sample apart (laid out by warp scheduler, see PU_MMA_WARP):
+//   walkers (12 warps)    stage the sample's trees, walk them with three threads per candidate (four trees in flight per
+//                         thread, numeric splits decided in FP32 on candidates rounded up -- exact, and off the FP64
+//                         pipe), leaf columns -> the row's bit mask, partial means on the way;
+//   epilogue (8 warps)    expand the masks into the one-hot int8 A operand IN TENSOR MEMORY (tcgen05.st; row = lane, four
+//                         K bytes per column) once the previous sample's MMAs are done; drain the accumulators:
+//                         z^T D_k z is the masked row sum of T_k = Z D_k, read as packed int16 pairs
+//                         (tcgen05.ld .pack::16b) and reduced with dp2a against the mask bytes;
+//   MMA issuer (1 thread) tcgen05.mma kind::i8 with A from TMEM, M = 128, N = 192 (two accumulators beside the A columns),
+//                         one (column tile, digit plane) item at a time, only the K tiles on or below the diagonal band;
+//   producer (1 thread)   streams the 24 KB digit tiles with the bulk-copy engine through a six-stage shared-memory ring,
+//                         free-running across samples.
 // The walk of sample s + 1 overlaps the MMAs of sample s.  No n_c x P matrix ever exists in memory.
+// Measured building blocks: scripts/umma_shapes.cu (MMA rate per shape, TMEM read rate), scripts/tma_feed.cu (bulk-copy feed).
 //
 // Replaces  scale - diag(K_xX K^-1 K_Xx)  of src/bark/tree_kernels/tree_gps.py:103-112.
 #include <algorithm>
@@ -28,18 +30,30 @@
 namespace bark {
 
 constexpr int PU_ROWS = 128;        // candidates per CTA (UMMA M)
-constexpr int PU_N = 256;           // Binv columns per accumulator tile (UMMA N); two TMEM buffers of 256 columns
+constexpr int PU_N_MAX = 192;       // Binv columns per accumulator tile (UMMA N).  TMEM holds the one-hot A operand (K_pad / 4
+                                    // columns) and two accumulators: N = 192 for K_pad <= 512, 160 above (pu_ntile)
 constexpr int PU_KB = 128;          // K bytes per operand tile (one SWIZZLE_128B atom row)
 constexpr int PU_SLICES = 7;        // base-256 digit planes
-constexpr int PU_MAX_STAGES = 4;    // ring stages; one stage = one K tile of one (column tile, digit plane)
+constexpr int PU_MAX_STAGES = 8;    // ring stages; one stage = one K tile of one (column tile, digit plane)
 constexpr int PU_WALK_GROUPS = 3;   // walker threads per candidate (trees t = g mod 3)
 constexpr int PU_WALK_WARPS = 4 * PU_WALK_GROUPS;
-constexpr int PU_EPI_WARPS = 8;     // two per TMEM lane quarter: each takes 128 of an item's 256 columns
-constexpr int PU_FIRST_EPI = 2, PU_FIRST_WALK = PU_FIRST_EPI + PU_EPI_WARPS;  // warp 0: MMA issue, warp 1: bulk-copy producer
-constexpr int PU_THREADS = 32 * (PU_FIRST_WALK + PU_WALK_WARPS);
-constexpr int PU_A_TILE = PU_ROWS * PU_KB;  // 16 KB
-constexpr int PU_B_TILE = PU_N * PU_KB;     // 32 KB
-constexpr int PU_RING_MAX = PU_MAX_STAGES * PU_B_TILE;
+constexpr int PU_EPI_WARPS = 8;     // two per TMEM lane quarter: each takes half of an item's columns
+// Warp roles are laid out by warp scheduler (warp % 4, which is also the TMEM lane quarter a warp may touch): the
+// MMA-issuing thread runs a latency-bound scalar loop, so its scheduler (0) hosts no walker -- only the producer and the two
+// light epilogue warps of quarter 0.
+//   warp 0: MMA issue      warp 4: bulk-copy producer      warps 16, 20: unused
+//   epilogue: warps 1-3, 5-7 (quarters 1-3, column halves 0 / 1) and 8, 12 (quarter 0)
+//   walkers: the twelve warps 9-11, 13-15, 17-19, 21-23
+constexpr int PU_MMA_WARP = 0, PU_PRODUCER_WARP = 4;
+constexpr int PU_THREADS = 32 * 24;
+__device__ __forceinline__ int pu_epilogue_half(int warp) {  // -1: not an epilogue warp
+    if ((warp & 3) == 0) return warp == 8 ? 0 : (warp == 12 ? 1 : -1);
+    return warp < 4 ? 0 : (warp < 8 ? 1 : -1);
+}
+__device__ __forceinline__ int pu_walker_index(int warp) {  // 0 .. 11, -1: not a walker
+    return (warp >= 9 && warp < 24 && (warp & 3) != 0) ? 3 * ((warp - 8) >> 2) + (warp & 3) - 1 : -1;
+}
+constexpr int PU_RING_MAX = PU_MAX_STAGES * PU_N_MAX * PU_KB;
 constexpr int PU_MAX_P = 768;
 
 __device__ __forceinline__ uint32_t pu_smem(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -48,21 +62,24 @@ __host__ __device__ __forceinline__ uint32_t pu_swizzle(uint32_t r, uint32_t kb)
     return g * 1024u + rr * 128u + ((chunk ^ rr) << 4) + b;
 }
 
-// First K tile of column tile nt that can hold an entry of the triangle k >= q (columns q of tile nt start at nt * PU_N).
-__host__ __device__ __forceinline__ int pu_kt_lo(int nt) { return nt * (PU_N / PU_KB); }
+// Accumulator width for kt K tiles: the A operand takes 32 kt TMEM columns, two accumulators share the other 512 - 32 kt.
+__host__ __device__ __forceinline__ int pu_ntile(int kt) { return kt <= 4 ? 192 : 160; }
+// First K tile of column tile nt that can hold an entry of the triangle k >= q (columns q of tile nt start at nt * ntile).
+__host__ __device__ __forceinline__ int pu_kt_lo(int nt, int ntile) { return (nt * ntile) / PU_KB; }
 
 struct PrepLayout {
     size_t off_table, off_tiles, off_scale, total;
-    int hi, kt, nt;
+    int hi, kt, nt, ntile;
 };
 __host__ __device__ inline PrepLayout prep_layout(int64_t samples, int64_t m, int slots, int p_max) {
     PrepLayout l;
     l.hi = slots;
     l.kt = (p_max + PU_KB - 1) / PU_KB;
-    l.nt = (l.kt * PU_KB + PU_N - 1) / PU_N;  // the last column tile may be half full (N = 128)
+    l.ntile = pu_ntile(l.kt);
+    l.nt = (l.kt * PU_KB + l.ntile - 1) / l.ntile;  // the last column tile may be narrower
     size_t o = 0;
     l.off_table = o; o = align256(o + (size_t)samples * m * slots * sizeof(WalkNode));
-    l.off_tiles = o; o = align256(o + (size_t)samples * l.nt * PU_SLICES * l.kt * PU_B_TILE);
+    l.off_tiles = o; o = align256(o + (size_t)samples * l.nt * PU_SLICES * l.kt * l.ntile * PU_KB);
     l.off_scale = o; o = align256(o + (size_t)samples * sizeof(double));
     l.total = o;
     return l;
@@ -82,9 +99,10 @@ __global__ void pu_table_kernel(WsLayout lay, const void* ws, bark_nodes_soa for
 }
 
 // Binv (lower triangle current) -> 7 digit planes, tiled [sample][nt][slice][kt] and pre-swizzled (K-major SW128);
-// only the K tiles kt >= pu_kt_lo(nt) of a column tile are written and later streamed
-__global__ void pu_slice_kernel(WsLayout lay, const void* ws, int kt_n, int nt_n, uint8_t* __restrict__ tiles,
+// only the K tiles kt >= pu_kt_lo(nt, ntile) of a column tile are written and later streamed
+__global__ void pu_slice_kernel(WsLayout lay, const void* ws, int kt_n, int nt_n, int ntile, uint8_t* __restrict__ tiles,
                                 double* __restrict__ scale_out) {
+    const size_t tile_bytes = (size_t)ntile * PU_KB;
     const int64_t sample = blockIdx.y;
     ChainView cv = chain_view(lay, const_cast<void*>(ws), sample);
     const double c = cv.sc->c;
@@ -94,22 +112,22 @@ __global__ void pu_slice_kernel(WsLayout lay, const void* ws, int kt_n, int nt_n
     const int shift = 53 - e;
     if (blockIdx.x == 0 && threadIdx.x == 0) scale_out[sample] = ldexp(1.0, -shift);
     const int64_t K = (int64_t)kt_n * PU_KB, Q = K, P = lay.P;
-    uint8_t* base = tiles + (size_t)sample * nt_n * PU_SLICES * kt_n * PU_B_TILE;
+    uint8_t* base = tiles + (size_t)sample * nt_n * PU_SLICES * kt_n * tile_bytes;
     for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < Q * K; idx += (int64_t)gridDim.x * blockDim.x) {
         const int64_t q = idx / K, k = idx % K;
-        const int64_t nt = q / PU_N, kt = k / PU_KB;
-        if (kt < pu_kt_lo((int)nt)) continue;  // tile above the diagonal band: never loaded
+        const int64_t nt = q / ntile, kt = k / PU_KB;
+        if (kt < pu_kt_lo((int)nt, ntile)) continue;  // tile above the diagonal band: never loaded
         // z^T Binv z = sum_i Binv_ii z_i + 2 sum_{k > q} Binv_kq z_k z_q: the operand is the triangle k >= q with the
         // off-diagonal entries doubled (|2 Binv_kq| < 2^(e+1): 55 signed bits, inside the 7 balanced digits' +-2^55)
         double v = 0.0;
         if (q < P && k < P && k >= q) v = (k == q) ? cv.Binv[q * P + q] : 2.0 * cv.Binv[k * P + q];
         long long x = llrint(ldexp(v, shift));
-        const uint32_t off = pu_swizzle((uint32_t)(q % PU_N), (uint32_t)(k % PU_KB));
+        const uint32_t off = pu_swizzle((uint32_t)(q % ntile), (uint32_t)(k % PU_KB));
 #pragma unroll
         for (int s = 0; s < PU_SLICES; ++s) {
             const long long dgt = ((x + 128) & 255) - 128;  // balanced digit in [-128, 127]
             x = (x - dgt) >> 8;
-            base[(((size_t)nt * PU_SLICES + s) * kt_n + kt) * PU_B_TILE + off] = (uint8_t)(int8_t)dgt;
+            base[(((size_t)nt * PU_SLICES + s) * kt_n + kt) * tile_bytes + off] = (uint8_t)(int8_t)dgt;
         }
     }
 }
@@ -220,15 +238,59 @@ __device__ __forceinline__ void pu_tmem_ld64_pack16(uint32_t taddr, uint32_t (&v
         : "r"(taddr)
         : "memory");
 }
+__device__ __forceinline__ void pu_tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {  // 16 columns, 32-bit
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void pu_tmem_ld32_pack16(uint32_t taddr, uint32_t (&v)[16]) {  // 32 columns -> 16 registers
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.pack::16b.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void pu_tmem_ld16_pack16(uint32_t taddr, uint32_t (&v)[8]) {  // 16 columns -> 8 registers
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x8.pack::16b.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void pu_tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};\n" ::"r"(taddr),
+        "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]),
+        "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+        : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem]: the A operand of an M = 128 kind::i8 MMA is 128 lanes x 8 columns (32 K bytes per row,
+// four per 32-bit column)
+__device__ __forceinline__ void pu_umma_i8_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(acc), "r"(0u)
+        : "memory");
+}
 __device__ __forceinline__ void pu_tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 struct PuSmem {
-    size_t off_a, off_ring, off_table, off_zmask, off_w, off_xs, off_xf, off_ft, off_mean, off_part, off_bars, total;
+    size_t off_ring, off_table, off_zmask, off_w, off_xs, off_xf, off_ft, off_mean, off_part, off_bars, total;
 };
 __host__ __device__ inline PuSmem pu_smem_layout(int m, int hi, int d, int kt, int ring_bytes, int nb) {
     PuSmem s;
     size_t o = 0;
-    s.off_a = o;      o += (size_t)kt * PU_A_TILE;
     s.off_ring = o;   o += (size_t)ring_bytes;
     s.off_table = o;  o = align256(o + (size_t)m * hi * sizeof(WalkNode));
     s.off_zmask = o;  o = align256(o + (size_t)nb * PU_ROWS * kt * 2 * 8);  // [mask buffer][64-column word][row]
@@ -241,16 +303,6 @@ __host__ __device__ inline PuSmem pu_smem_layout(int m, int hi, int d, int kt, i
     s.off_bars = o;   o = align256(o + (size_t)(2 * PU_MAX_STAGES + 9) * 8 + 16);
     s.total = o;
     return s;
-}
-
-// 16 mask bits -> 16 bytes of 0 / 1 (x * 0x00204081 spreads 4 bits over the low bits of 4 bytes)
-__device__ __forceinline__ uint4 pu_expand16(uint32_t b) {
-    uint4 r;
-    r.x = ((b & 0xFu) * 0x00204081u) & 0x01010101u;
-    r.y = (((b >> 4) & 0xFu) * 0x00204081u) & 0x01010101u;
-    r.z = (((b >> 8) & 0xFu) * 0x00204081u) & 0x01010101u;
-    r.w = (((b >> 12) & 0xFu) * 0x00204081u) & 0x01010101u;
-    return r;
 }
 
 #ifdef BARK_PHASE_TIMING
@@ -268,13 +320,12 @@ __device__ __forceinline__ void pu_named_sync(int id, int threads) { asm volatil
 
 __global__ void __launch_bounds__(PU_THREADS, 1)
 predict_umma_kernel(WsLayout lay, const void* ws, const WalkNode* __restrict__ table, const uint8_t* __restrict__ tiles,
-                    const double* __restrict__ scales, int hi, int kt_n, int nt_n, int ring_bytes, int nb,
+                    const double* __restrict__ scales, int hi, int kt_n, int nt_n, int ntile, int ring_bytes, int nb,
                     const double* __restrict__ cand,
-                    int64_t n_c, double* __restrict__ mu, double* __restrict__ var, int pu_exp) {
+                    int64_t n_c, double* __restrict__ mu, double* __restrict__ var) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     const int d = (int)lay.d, m = (int)lay.m;
     const PuSmem sl = pu_smem_layout(m, hi, d, kt_n, ring_bytes, nb);  // nb = 2: the walk runs one sample ahead; 1: tight shared memory
-    unsigned char* a_tiles = smem_raw + sl.off_a;
     unsigned char* ring = smem_raw + sl.off_ring;
     WalkNode* tb = reinterpret_cast<WalkNode*>(smem_raw + sl.off_table);
     unsigned long long* zmask = reinterpret_cast<unsigned long long*>(smem_raw + sl.off_zmask);  // [parity][word][row]
@@ -292,7 +343,10 @@ predict_umma_kernel(WsLayout lay, const void* ws, const WalkNode* __restrict__ t
     uint64_t* mask_free = mask_ready + 2;            // [2] epilogue -> walkers: the sample that used the buffer is finished
     uint64_t* a_ready = mask_free + 2;               // [1] epilogue -> MMA: the A operand of the next sample is in place
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_ready + 1);
-    const int nstages = min(PU_MAX_STAGES, ring_bytes / PU_B_TILE);
+    const int tile_bytes = ntile * PU_KB;  // one ring stage: ntile Binv columns x 128 K bytes
+    const int nstages = min(PU_MAX_STAGES, ring_bytes / tile_bytes);
+    // TMEM columns: [0, 32 kt) the one-hot A operand (row = lane, four K bytes per column), the two accumulators at the top
+    const int acc_base = 512 - 2 * ntile;
     const int nwords = kt_n * 2;  // 64-column mask words per candidate row
     const int mask_words = PU_ROWS * nwords;
 
@@ -325,7 +379,7 @@ predict_umma_kernel(WsLayout lay, const void* ws, const WalkNode* __restrict__ t
         pu_mbar_init(a_ready, PU_EPI_WARPS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 0) {
+    if (warp == PU_MMA_WARP) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(pu_smem(tmem_slot)), "r"(512u)
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -346,9 +400,10 @@ predict_umma_kernel(WsLayout lay, const void* ws, const WalkNode* __restrict__ t
     const uint32_t tmem_d = *tmem_slot;
     const int items = nt_n * PU_SLICES;
     (void)items;
-    const int last_cols = kt_n * PU_KB - (nt_n - 1) * PU_N;  // columns of the last column tile (128 or 256)
+    const int last_cols = kt_n * PU_KB - (nt_n - 1) * ntile;  // columns of the last column tile
 
-    if (warp == 1) {
+    const int eh = pu_epilogue_half(warp), wi = pu_walker_index(warp);
+    if (warp == PU_PRODUCER_WARP) {
         // ================= producer: digit tiles of sample after sample, items in order, K tiles kt >= pu_kt_lo(nt).
         // (Both single-thread loops below keep their bookkeeping incremental -- ring position and phase, source pointer,
         // descriptors by addition: one lone thread runs ~5 cycles per dependent instruction, and an integer division by
@@ -360,18 +415,18 @@ predict_umma_kernel(WsLayout lay, const void* ws, const WalkNode* __restrict__ t
             for (int si = 0; si < ns; ++si) {
                 const int64_t sample = s_lo + si;
                 unsigned* st = &chain_view(lay, const_cast<void*>(ws), sample).sc->status;
-                const uint8_t* src_item = tiles + (size_t)sample * nt_n * PU_SLICES * kt_n * PU_B_TILE;
+                const uint8_t* src_item = tiles + (size_t)sample * nt_n * PU_SLICES * kt_n * tile_bytes;
                 for (int nt = 0; nt < nt_n; ++nt) {
-                    const uint32_t bytes = (uint32_t)((nt == nt_n - 1) ? last_cols : PU_N) * PU_KB;
-                    const int kt_lo = pu_kt_lo(nt);
-                    for (int sl_ = 0; sl_ < PU_SLICES; ++sl_, src_item += (size_t)kt_n * PU_B_TILE) {
-                        const uint8_t* src = src_item + (size_t)kt_lo * PU_B_TILE;
-                        for (int kt = kt_lo; kt < kt_n; ++kt, src += PU_B_TILE) {
+                    const uint32_t bytes = (uint32_t)((nt == nt_n - 1) ? last_cols : ntile) * PU_KB;
+                    const int kt_lo = pu_kt_lo(nt, ntile);
+                    for (int sl_ = 0; sl_ < PU_SLICES; ++sl_, src_item += (size_t)kt_n * tile_bytes) {
+                        const uint8_t* src = src_item + (size_t)kt_lo * tile_bytes;
+                        for (int kt = kt_lo; kt < kt_n; ++kt, src += tile_bytes) {
                             PU_T0();
                             if (!first_lap) pu_mbar_wait(empty_bar + stage, phase, st);
                             PU_ACC(0);
                             pu_mbar_expect_tx(full_bar + stage, bytes);
-                            pu_bulk_g2s(ring + (size_t)stage * PU_B_TILE, src, bytes, full_bar + stage);
+                            pu_bulk_g2s(ring + (size_t)stage * tile_bytes, src, bytes, full_bar + stage);
                             PU_ACC(1);
                             if (++stage == nstages) {
                                 stage = 0;
@@ -385,25 +440,28 @@ predict_umma_kernel(WsLayout lay, const void* ws, const WalkNode* __restrict__ t
             PU_REPORT("pu_producer per sample: wait_empty %lld issue %lld\n", pu_w[0] / ns, pu_w[1] / ns);
         }
         __syncwarp();
-    } else if (warp == 0) {
-        // ================= MMA issuer: item = (column tile, digit plane) into TMEM buffer (running item index) & 1
+    } else if (warp == PU_MMA_WARP) {
+        // ================= MMA issuer: item = (column tile, digit plane) into TMEM buffer (running item index) & 1.
+        // (Tried and dropped: doing the next tile's barrier waits between the second and third MMA of the current tile --
+        // 9.6 instead of 10.8 M points/s; a flattened tile iterator -- 8.0 M: this lone thread is latency-bound on its own
+        // scalar instructions, anything added to the loop costs more than it hides.)
         if (lane == 0) {
             int stage = 0;
             uint32_t full_phase = 0;
             uint32_t git = 0;  // running item index: TMEM buffer git & 1, its use count git >> 1
             const uint64_t desc_hi = (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);  // pu_desc_sw128 without the address
-            const uint64_t a_desc0 = desc_hi | (uint64_t)((pu_smem(a_tiles) >> 4) & 0x3FFFu);
             const uint64_t b_desc0 = desc_hi | (uint64_t)((pu_smem(ring) >> 4) & 0x3FFFu);
-            const uint32_t idesc_full = pu_idesc_i8(PU_ROWS, PU_N), idesc_last = pu_idesc_i8(PU_ROWS, last_cols);
+            const uint32_t idesc_full = pu_idesc_i8(PU_ROWS, ntile), idesc_last = pu_idesc_i8(PU_ROWS, last_cols);
+            const uint32_t b_step = (uint32_t)(tile_bytes >> 4);
             for (int si = 0; si < ns; ++si) {
                 unsigned* st = &chain_view(lay, const_cast<void*>(ws), s_lo + si).sc->status;
                 PU_T0();
-                pu_mbar_wait(a_ready, (uint32_t)(si & 1), st);  // A operand of this sample written (and proxy-fenced)
+                pu_mbar_wait(a_ready, (uint32_t)(si & 1), st);  // A operand of this sample written into TMEM
                 PU_ACC(0);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 for (int nt = 0; nt < nt_n; ++nt) {
                     const uint32_t idesc = (nt == nt_n - 1) ? idesc_last : idesc_full;
-                    const int kt_lo = pu_kt_lo(nt);
+                    const int kt_lo = pu_kt_lo(nt, ntile);
                     for (int sl_ = 0; sl_ < PU_SLICES; ++sl_) {
                         const uint32_t buf = git & 1u, use = git >> 1;
                         PU_T0();
@@ -411,19 +469,20 @@ predict_umma_kernel(WsLayout lay, const void* ws, const WalkNode* __restrict__ t
                         PU_ACC(1);
                         PU_TL(0, si, nt * PU_SLICES + sl_);
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                        const uint32_t d_addr = tmem_d + buf * PU_N;
-                        uint64_t a_desc = a_desc0 + (uint64_t)(kt_lo * (PU_A_TILE >> 4));
-                        for (int kt = kt_lo; kt < kt_n; ++kt, a_desc += (PU_A_TILE >> 4)) {
+                        const uint32_t d_addr = tmem_d + (uint32_t)acc_base + buf * (uint32_t)ntile;
+                        uint32_t a_addr = tmem_d + (uint32_t)(kt_lo * (PU_KB / 4));  // 32 A columns per K tile, 8 per MMA
+                        for (int kt = kt_lo; kt < kt_n; ++kt, a_addr += PU_KB / 4) {
                             PU_T0();
                             pu_mbar_wait(full_bar + stage, full_phase, st);
                             PU_ACC(2);
                             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                            const uint64_t b_desc = b_desc0 + (uint64_t)(stage * (PU_B_TILE >> 4));
-                            pu_umma_i8(d_addr, a_desc, b_desc, idesc, kt > kt_lo ? 1u : 0u);
-                            pu_umma_i8(d_addr, a_desc + 2, b_desc + 2, idesc, 1u);
-                            pu_umma_i8(d_addr, a_desc + 4, b_desc + 4, idesc, 1u);
-                            pu_umma_i8(d_addr, a_desc + 6, b_desc + 6, idesc, 1u);
-                            pu_commit(empty_bar + stage);
+                            const uint64_t b_desc = b_desc0 + (uint64_t)((uint32_t)stage * b_step);
+                            pu_umma_i8_ts(d_addr, a_addr, b_desc, idesc, kt > kt_lo ? 1u : 0u);
+                            pu_umma_i8_ts(d_addr, a_addr + 8, b_desc + 2, idesc, 1u);
+                            pu_umma_i8_ts(d_addr, a_addr + 16, b_desc + 4, idesc, 1u);
+                            pu_umma_i8_ts(d_addr, a_addr + 24, b_desc + 6, idesc, 1u);
+                            // the stage of an item's last K tile is released by the epilogue when it sees acc_full
+                            if (kt + 1 < kt_n) pu_commit(empty_bar + stage);
                             PU_ACC(3);
                             if (++stage == nstages) { stage = 0; full_phase ^= 1u; }
                         }
@@ -437,9 +496,9 @@ predict_umma_kernel(WsLayout lay, const void* ws, const WalkNode* __restrict__ t
                       pu_w[3] / ns);
         }
         __syncwarp();
-    } else if (warp >= PU_FIRST_WALK) {
+    } else if (wi >= 0) {
         // ================= walkers: PU_WALK_GROUPS threads per candidate, one sample ahead of the MMAs
-        const int wt = tid - PU_FIRST_WALK * 32;  // 0 .. 32 * PU_WALK_WARPS - 1
+        const int wt = wi * 32 + lane;  // 0 .. 32 * PU_WALK_WARPS - 1
         const int wg = wt / PU_ROWS, row = wt % PU_ROWS;
         constexpr int WALKERS = 32 * PU_WALK_WARPS;
         for (int si = 0; si < ns; ++si) {
@@ -459,7 +518,7 @@ predict_umma_kernel(WsLayout lay, const void* ws, const WalkNode* __restrict__ t
             pu_named_sync(2, WALKERS);
             PU_ACC(1);
             double mean = 0.0;
-            if (row < np && !(pu_exp & 1)) {
+            if (row < np) {
                 const double* xp = xs + row;
                 const float* xfp = xf + row;
                 unsigned* zm32 = reinterpret_cast<unsigned*>(zm);
@@ -509,31 +568,32 @@ predict_umma_kernel(WsLayout lay, const void* ws, const WalkNode* __restrict__ t
             PU_ACC(2);
         }
         if (wt == 0) PU_REPORT("pu_walker per sample: wait_mask_free %lld stage %lld walk %lld\n", pu_w[0] / ns, pu_w[1] / ns, pu_w[2] / ns);
-    } else {
+    } else if (eh >= 0) {
         // ================= epilogue warps: A operand of the next sample, masked int32 row sums of every digit plane
-        const int ew = warp - PU_FIRST_EPI;
-        const int quarter = warp & 3, half = ew >> 2;  // TMEM lane quarter of this warp; which 128 of an item's 256 columns
+        const int quarter = warp & 3, half = eh;  // TMEM lane quarter of this warp; which half of an item's columns
         const int row = 32 * quarter + lane;
-        const int et = tid - PU_FIRST_EPI * 32;  // 0 .. 255
+        const int et = (half * 4 + quarter) * 32 + lane;  // 0 .. 255
         constexpr int EPI = 32 * PU_EPI_WARPS;
         const bool narrow = (m * 128 <= 32767);  // |T_k| <= 128 m fits int16
 
         auto build_a = [&](int si) {
-            // one-hot A operand (K-major, SWIZZLE_128B) from the masks of sample si: one 16-byte chunk per thread and step
+            // one-hot A operand of sample si into TMEM from the masks
             unsigned* st = &chain_view(lay, const_cast<void*>(ws), s_lo + si).sc->status;
             PU_T0();
             pu_mbar_wait(mask_ready + si % nb, (uint32_t)((si / nb) & 1), st);
             PU_ACC(0);
             const unsigned long long* zm = zmask + (size_t)(si % nb) * mask_words;
-            const int chunks_per_row = kt_n * 8;
-            for (int e = et; e < PU_ROWS * chunks_per_row; e += EPI) {
-                const int r_ = e % PU_ROWS, ch = e / PU_ROWS;  // rows fastest: consecutive mask words, 8 swizzled chunks per group
-                const uint32_t bits = (uint32_t)(zm[(size_t)(ch >> 2) * PU_ROWS + r_] >> ((ch & 3) * 16)) & 0xFFFFu;
-                const uint32_t r = (uint32_t)r_, c = (uint32_t)(ch & 7);
-                unsigned char* dst = a_tiles + (size_t)(ch >> 3) * PU_A_TILE + (r >> 3) * 1024u + (r & 7) * 128u + ((c ^ (r & 7)) << 4);
-                *reinterpret_cast<uint4*>(dst) = pu_expand16(bits);
+            // thread = candidate row = TMEM lane of its warp's quarter; one 64-bit mask word = 64 K bytes = 16 columns per
+            // tcgen05.st; the two warps of a quarter share the words
+            for (int wd = half * kt_n; wd < (half + 1) * kt_n; ++wd) {
+                const unsigned long long bits = zm[(size_t)wd * PU_ROWS + row];
+                uint32_t v[16];
+#pragma unroll
+                for (int c = 0; c < 16; ++c) v[c] = (((uint32_t)(bits >> (4 * c)) & 0xFu) * 0x00204081u) & 0x01010101u;
+                pu_tmem_st16(tmem_d + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(wd * 16), v);
             }
-            asm volatile("fence.proxy.async;" ::: "memory");  // generic writes of the A operand -> tensor-core (async proxy) reads
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0) pu_mbar_arrive(a_ready);
             PU_ACC(1);
@@ -541,6 +601,7 @@ predict_umma_kernel(WsLayout lay, const void* ws, const WalkNode* __restrict__ t
 
         if (ns > 0) build_a(0);
         int git = 0;
+        int ep_stage = 0;  // ring position of the next item's first K tile (same walk as the producer / MMA issuer)
         for (int si = 0; si < ns; ++si) {
             const int64_t sample = s_lo + si;
             const int par = si % nb;
@@ -550,12 +611,24 @@ predict_umma_kernel(WsLayout lay, const void* ws, const WalkNode* __restrict__ t
             int acc[PU_SLICES];
 #pragma unroll
             for (int s = 0; s < PU_SLICES; ++s) acc[s] = 0;
+            const int hcols = ntile / 2;  // this warp's share of an item's columns: 96 (64 + 32) or 80 (64 + 16)
             for (int nt = 0; nt < nt_n; ++nt) {
-                const int ncols = (nt == nt_n - 1) ? last_cols : PU_N;
-                // this warp's 128 columns of the item = two 64-column mask words of its row
-                const int w0 = nt * (PU_N / 64) + 2 * half;
-                const unsigned long long bits0 = (half * 128 < ncols) ? zm[(size_t)w0 * PU_ROWS + row] : 0ull;
-                const unsigned long long bits1 = (half * 128 + 64 < ncols) ? zm[(size_t)(w0 + 1) * PU_ROWS + row] : 0ull;
+                const int ncols = (nt == nt_n - 1) ? last_cols : ntile;
+                // the row's mask bits of this warp's columns [o, o + hcols), those beyond the tile's width cleared
+                const int o = nt * ntile + half * hcols;
+                const int valid = max(0, min(hcols, ncols - half * hcols));
+                const int item_tiles = kt_n - pu_kt_lo(nt, ntile);
+                unsigned long long bits0, bits1;
+                {
+                    const int wi = o >> 6, sh = o & 63;
+                    const unsigned long long a = (wi < nwords) ? zm[(size_t)wi * PU_ROWS + row] : 0ull;
+                    const unsigned long long b = (wi + 1 < nwords) ? zm[(size_t)(wi + 1) * PU_ROWS + row] : 0ull;
+                    const unsigned long long c = (wi + 2 < nwords) ? zm[(size_t)(wi + 2) * PU_ROWS + row] : 0ull;
+                    bits0 = sh ? ((a >> sh) | (b << (64 - sh))) : a;
+                    bits1 = sh ? ((b >> sh) | (c << (64 - sh))) : b;
+                    if (valid < 64) { bits0 = valid > 0 ? (bits0 & ((1ull << valid) - 1ull)) : 0ull; bits1 = 0ull; }
+                    else bits1 = (valid > 64) ? (bits1 & ((1ull << (valid - 64)) - 1ull)) : 0ull;
+                }
 #pragma unroll
                 for (int s = 0; s < PU_SLICES; ++s, ++git) {
                     const int buf = git & 1, use = git >> 1;
@@ -563,36 +636,51 @@ predict_umma_kernel(WsLayout lay, const void* ws, const WalkNode* __restrict__ t
                     pu_mbar_wait(acc_full + buf, (uint32_t)(use & 1), st);
                     PU_ACC(2);
                     if (et == 0) PU_TL(2, si, nt * PU_SLICES + s);
+                    {   // the item's MMAs are complete: release the ring stage of its last K tile
+                        ep_stage += item_tiles;
+                        while (ep_stage >= nstages) ep_stage -= nstages;
+                        if (et == 0) pu_mbar_arrive(empty_bar + (ep_stage == 0 ? nstages - 1 : ep_stage - 1));
+                    }
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const uint32_t taddr = tmem_d + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * PU_N + 128 * half);
+                    const uint32_t taddr = tmem_d + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc_base + buf * ntile + half * hcols);
                     int a0 = 0, a1 = 0, a2 = 0, a3 = 0;
-                    if (__any_sync(0xffffffffu, (bits0 | bits1) != 0ull) || (pu_exp & 2)) {
+                    if (__any_sync(0xffffffffu, (bits0 | bits1) != 0ull)) {
                         if (narrow) {
-                            // packed loads (two int16 columns per register), both issued before the single wait; one dp2a
+                            // packed loads (two int16 columns per register), all issued before the single wait; one dp2a
                             // per register against the row's 0 / 1 mask bytes
-                            uint32_t v0[32], v1[32];
+                            uint32_t v0[32], v1[16];
                             pu_tmem_ld64_pack16(taddr, v0);
-                            pu_tmem_ld64_pack16(taddr + 64, v1);
+                            if (hcols == 96) {
+                                pu_tmem_ld32_pack16(taddr + 64, v1);
+                            } else {
+                                uint32_t v8[8];
+                                pu_tmem_ld16_pack16(taddr + 64, v8);
+#pragma unroll
+                                for (int r = 0; r < 8; ++r) { v1[r] = v8[r]; v1[8 + r] = 0u; }
+                            }
                             pu_tmem_wait_ld();
                             if (et == 0) PU_TL(3, si, nt * PU_SLICES + s);
 #pragma unroll
                             for (int r = 0; r < 16; ++r) {
                                 const uint32_t m0 = (((uint32_t)(bits0 >> (4 * r)) & 0xFu) * 0x00204081u) & 0x01010101u;
-                                const uint32_t m1 = (((uint32_t)(bits1 >> (4 * r)) & 0xFu) * 0x00204081u) & 0x01010101u;
                                 a0 = __dp2a_lo((int)v0[2 * r], (int)m0, a0);
                                 a1 = __dp2a_hi((int)v0[2 * r + 1], (int)m0, a1);
+                            }
+#pragma unroll
+                            for (int r = 0; r < 8; ++r) {
+                                const uint32_t m1 = (((uint32_t)(bits1 >> (4 * r)) & 0xFu) * 0x00204081u) & 0x01010101u;
                                 a2 = __dp2a_lo((int)v1[2 * r], (int)m1, a2);
                                 a3 = __dp2a_hi((int)v1[2 * r + 1], (int)m1, a3);
                             }
                         } else {
-#pragma unroll 1
-                            for (int j = 0; j < 4; ++j) {
-                                uint32_t v[32];
-                                pu_tmem_ld32(taddr + 32 * j, v);
+                            // forests of more than 255 trees: 32-bit accumulators, 16 columns at a time
+                            for (int j = 0; j * 16 < valid; ++j) {
+                                uint32_t v[16];
+                                pu_tmem_ld16(taddr + 16 * j, v);
                                 pu_tmem_wait_ld();
-                                const uint32_t b = (uint32_t)((j < 2 ? bits0 : bits1) >> (32 * (j & 1)));
+                                const uint32_t b = (uint32_t)((j < 4 ? bits0 : bits1) >> (16 * (j & 3))) & 0xFFFFu;
 #pragma unroll
-                                for (int c = 0; c < 32; ++c) a0 += (int)v[c] * (int)((b >> c) & 1u);
+                                for (int c = 0; c < 16; ++c) a0 += (int)v[c] * (int)((b >> c) & 1u);
                             }
                         }
                     }
@@ -635,7 +723,7 @@ predict_umma_kernel(WsLayout lay, const void* ws, const WalkNode* __restrict__ t
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(512u) : "memory");
+    if (warp == PU_MMA_WARP) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(512u) : "memory");
 #ifdef BARK_PHASE_TIMING
     if (pu_trace && tid == 0 && ns > 20)
         for (int it = 0; it < items && it < 16; ++it)
@@ -667,7 +755,7 @@ int bark_predict_prepare(const bark_mcmc_dims* dims, const void* workspace, bark
     unsigned char* base = (unsigned char*)prep;
     pu_table_kernel<<<148 * 2, 256, 0, st>>>(lay, workspace, forest, slots, (WalkNode*)(base + pl.off_table));
     dim3 grid(148, (unsigned)dims->chains);
-    pu_slice_kernel<<<grid, 256, 0, st>>>(lay, workspace, pl.kt, pl.nt, base + pl.off_tiles, (double*)(base + pl.off_scale));
+    pu_slice_kernel<<<grid, 256, 0, st>>>(lay, workspace, pl.kt, pl.nt, pl.ntile, base + pl.off_tiles, (double*)(base + pl.off_scale));
     BARK_LAUNCH_CHECK();
     return BARK_OK;
 }
@@ -683,7 +771,7 @@ int bark_predict_umma(const bark_mcmc_dims* dims, const void* workspace, const v
     BARK_CHECK_ARG(dims->chains <= 65535, "too many samples per call");
     const WsLayout lay = make_layout(*dims);
     const PrepLayout pl = prep_layout(dims->chains, dims->m, slots, p_max);
-    const int stage_bytes = PU_B_TILE;
+    const int stage_bytes = pl.ntile * PU_KB;
     // two mask buffers (the walk runs a sample ahead of the MMAs) when they fit beside a ring of >= 2 stages, else one
     int nb = 2;
     size_t fixed = pu_smem_layout((int)lay.m, slots, (int)lay.d, pl.kt, 0, nb).total;
@@ -702,7 +790,7 @@ int bark_predict_umma(const bark_mcmc_dims* dims, const void* workspace, const v
     dim3 grid((unsigned)tiles_n, (unsigned)ysplit);
     predict_umma_kernel<<<grid, PU_THREADS, sl.total, (cudaStream_t)stream>>>(
         lay, workspace, (const WalkNode*)(base + pl.off_table), base + pl.off_tiles, (const double*)(base + pl.off_scale),
-        slots, pl.kt, pl.nt, ring_bytes, nb, candidates, n_c, mu, var, getenv("BARK_PU_EXP") ? atoi(getenv("BARK_PU_EXP")) : 0);
+        slots, pl.kt, pl.nt, pl.ntile, ring_bytes, nb, candidates, n_c, mu, var);
     BARK_LAUNCH_CHECK();
     return BARK_OK;
 }

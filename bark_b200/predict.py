@@ -55,15 +55,17 @@ class PosteriorState:
     @property
     def umma_ops_per_candidate_sample(self):
         """int8 multiply-adds x 2 that the tensor-core path executes per (candidate, posterior sample): 7 digit planes of
-        the triangular operand -- column tiles of 256 (the last may be 128), K tiles of 128 from the diagonal down
+        the triangular operand -- column tiles of 192 (160 above 512 columns; the last may be narrower), K tiles of 128 from the
+        diagonal band down
         (csrc/predict_umma.cu, pu_kt_lo)."""
         if not self.k_pad:
             return None
         kt = self.k_pad // 128
+        ntile = 192 if kt <= 4 else 160  # pu_ntile: accumulator width beside the A operand in TMEM
         ops, nt = 0, 0
-        while nt * 256 < self.k_pad:
-            ncols = min(256, self.k_pad - nt * 256)
-            ops += 2 * 7 * ncols * 128 * (kt - 2 * nt)
+        while nt * ntile < self.k_pad:
+            ncols = min(ntile, self.k_pad - nt * ntile)
+            ops += 2 * 7 * ncols * 128 * (kt - (nt * ntile) // 128)
             nt += 1
         return ops
 

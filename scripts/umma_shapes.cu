@@ -89,7 +89,7 @@ __global__ void __launch_bounds__(128, 1) k(int iters, int group, long long* out
 
 // Fresh operands: B rotates through 4 x 32 KB stages and A through 4 tiles (no operand-collector reuse), and the
 // accumulator alternates between NACC TMEM buffers (consecutive MMAs into one accumulator form a dependent chain).
-template <bool TS, int N, int NACC>
+template <bool TS, int N, int NACC, int CE = 0>
 __global__ void __launch_bounds__(128, 1) k_rot(int iters, long long* out, int commit_every = 0) {
     extern __shared__ __align__(1024) unsigned char sm[];  // A: 4 x 16 KB, B: 4 x 32 KB
     __shared__ uint64_t bar, bar2;
@@ -130,7 +130,7 @@ __global__ void __launch_bounds__(128, 1) k_rot(int iters, long long* out, int c
             if (TS) mma_ts(dcol, tmem_d + stage * 32 + k4 * 8, desc_sw128(b_base + stage * 32768 + k4 * 32), idesc, acc);
             else mma_ss(dcol, desc_sw128(a_base + stage * 16384 + k4 * 32), desc_sw128(b_base + stage * 32768 + k4 * 32), idesc, acc);
             // a commit nobody waits for (the ring-slot release of a pipelined kernel): does it slow the MMA stream?
-            if (commit_every > 0 && ((it + 1) & (commit_every - 1)) == 0)
+            if (CE > 0 && ((it + 1) & (CE - 1)) == 0)
                 asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar2)) : "memory");
         }
         asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
@@ -143,13 +143,13 @@ __global__ void __launch_bounds__(128, 1) k_rot(int iters, long long* out, int c
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(512u) : "memory");
 }
 
-template <bool TS, int N, int NACC>
-static void run_rot(const char* name, long long* d, int commit_every = 0) {
+template <bool TS, int N, int NACC, int CE = 0>
+static void run_rot(const char* name, long long* d, int commit_every = CE) {
     const int iters = 4096, smem = 4 * 16384 + 4 * 32768 + 1024;
-    cudaFuncSetAttribute(k_rot<TS, N, NACC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    k_rot<TS, N, NACC><<<148, 128, smem>>>(iters, d, commit_every);
+    cudaFuncSetAttribute(k_rot<TS, N, NACC, CE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    k_rot<TS, N, NACC, CE><<<148, 128, smem>>>(iters, d, commit_every);
     cudaDeviceSynchronize();
-    k_rot<TS, N, NACC><<<148, 128, smem>>>(iters, d, commit_every);
+    k_rot<TS, N, NACC, CE><<<148, 128, smem>>>(iters, d, commit_every);
     cudaError_t e = cudaDeviceSynchronize();
     long long c = 0;
     cudaMemcpy(&c, d, 8, cudaMemcpyDeviceToHost);
@@ -256,10 +256,10 @@ int main() {
     run<false, 256>("SS, commit + wait every 16", 16, d);
     run<false, 256>("SS, commit + wait every 4", 4, d);
     run_rot<false, 256, 1>("SS", d);
-    run_rot<false, 256, 1>("SS", d, 4);
-    run_rot<false, 256, 1>("SS", d, 8);
-    run_rot<false, 256, 1>("SS", d, 16);
-    run_rot<false, 128, 1>("SS", d, 4);
+    run_rot<false, 256, 1, 4>("SS", d);
+    run_rot<false, 256, 1, 1>("SS", d);
+    run_rot<true, 192, 2, 4>("TS", d);
+    run_rot<true, 128, 2, 4>("TS", d);
     run_rot<true, 256, 1>("TS", d);
     run_rot<false, 128, 1>("SS", d);
     run_rot<false, 128, 2>("SS", d);
