@@ -80,6 +80,8 @@ SIGNATURES = {
     "bark_predict_prepare": (c_int, [C.POINTER(McmcDims), c_void_p, NodesSoA, c_int32, c_int32, c_void_p, c_void_p]),
     "bark_predict_umma": (c_int, [C.POINTER(McmcDims), c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_int64, c_void_p,
                                   c_void_p, c_void_p]),
+    "bark_predict_umma_mixture": (c_int, [C.POINTER(McmcDims), c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_int64, c_double,
+                                          c_double, c_int, c_void_p, c_void_p, c_void_p]),
     "bark_predict_mixture": (c_int, [C.POINTER(McmcDims), c_void_p, c_void_p, c_void_p, c_int64, c_double, c_double,
                                      c_int, c_void_p, c_void_p, c_void_p]),
 }

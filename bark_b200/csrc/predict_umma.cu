@@ -322,7 +322,11 @@ __global__ void __launch_bounds__(PU_THREADS, 1)
 predict_umma_kernel(WsLayout lay, const void* ws, const WalkNode* __restrict__ table, const uint8_t* __restrict__ tiles,
                     const double* __restrict__ scales, int hi, int kt_n, int nt_n, int ntile, int ring_bytes, int nb,
                     const double* __restrict__ cand,
-                    int64_t n_c, double* __restrict__ mu, double* __restrict__ var) {
+                    int64_t n_c, double* __restrict__ mu, double* __restrict__ var, int mix, double y_mean, double y_std,
+                    int add_noise) {
+    // mix != 0 (only when this CTA covers every sample, gridDim.y == 1): mu / var (n_c) receive the moments of the
+    // mixture over the samples after un-standardisation, accumulated in registers in sample order -- the arithmetic of
+    // predict_mixture_kernel (csrc/predict.cu) without the (samples, n_c) round trip through memory
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     const int d = (int)lay.d, m = (int)lay.m;
     const PuSmem sl = pu_smem_layout(m, hi, d, kt_n, ring_bytes, nb);  // nb = 2: the walk runs one sample ahead; 1: tight shared memory
@@ -600,6 +604,7 @@ predict_umma_kernel(WsLayout lay, const void* ws, const WalkNode* __restrict__ t
         };
 
         if (ns > 0) build_a(0);
+        double mix_sm = 0.0, mix_s2 = 0.0;
         int git = 0;
         int ep_stage = 0;  // ring position of the next item's first K tile (same walk as the producer / MMA issuer)
         for (int si = 0; si < ns; ++si) {
@@ -709,14 +714,28 @@ predict_umma_kernel(WsLayout lay, const void* ws, const WalkNode* __restrict__ t
                 double mean = 0.0;
 #pragma unroll
                 for (int g = 0; g < PU_WALK_GROUPS; ++g) mean += meanp[((size_t)par * PU_WALK_GROUPS + g) * PU_ROWS + row];
-                const int64_t o = sample * n_c + p0 + row;
-                mu[o] = mean;
-                var[o] = cv.sc->sig * (tsum * scales[sample]);
+                const double v = cv.sc->sig * (tsum * scales[sample]);
+                if (mix) {
+                    const double mj = mean * y_std + y_mean;
+                    double vj = v * (y_std * y_std);
+                    if (add_noise) vj += cv.sc->noise;
+                    mix_sm += mj;
+                    mix_s2 += vj + mj * mj;
+                } else {
+                    const int64_t o = sample * n_c + p0 + row;
+                    mu[o] = mean;
+                    var[o] = v;
+                }
             }
             pu_named_sync(1, EPI);  // accp / meanp / masks of this sample are no longer needed
             if (lane == 0) pu_mbar_arrive(mask_free + par);
             PU_ACC(4);
             if (nb == 1 && si + 1 < ns) build_a(si + 1);
+        }
+        if (mix && half == 0 && row < np) {
+            const double e = mix_sm / (double)S;
+            mu[p0 + row] = e;
+            var[p0 + row] = mix_s2 / (double)S - e * e;
         }
         if (et == 0) PU_REPORT("pu_epilogue per sample: wait_mask_ready %lld build_a %lld wait_acc_full %lld drain %lld output %lld\n", pu_w[0] / ns,
                                pu_w[1] / ns, pu_w[2] / ns, pu_w[3] / ns, pu_w[4] / ns);
@@ -760,15 +779,10 @@ int bark_predict_prepare(const bark_mcmc_dims* dims, const void* workspace, bark
     return BARK_OK;
 }
 
-// per-sample moments (samples, n_c) into mu / var
-int bark_predict_umma(const bark_mcmc_dims* dims, const void* workspace, const void* prep, int32_t slots, int32_t p_max,
-                      const double* candidates, int64_t n_c, double* mu, double* var, void* stream) {
-    BARK_CHECK_ARG(dims && workspace && prep, "null pointer");
-    BARK_CHECK_ARG(n_c >= 0, "n_c < 0");
-    if (n_c == 0) return BARK_OK;
-    BARK_CHECK_ARG(candidates && mu && var, "null pointer");
-    BARK_CHECK_ARG(slots >= 1 && slots <= 255 && p_max >= 1 && p_max <= PU_MAX_P, "slots / p_max out of range");
-    BARK_CHECK_ARG(dims->chains <= 65535, "too many samples per call");
+static int predict_umma_launch(const char* __func_name, const bark_mcmc_dims* dims, const void* workspace, const void* prep, int32_t slots,
+                               int32_t p_max, const double* candidates, int64_t n_c, double* mu, double* var, int mix, double y_mean,
+                               double y_std, int add_noise, void* stream) {
+    (void)__func_name;
     const WsLayout lay = make_layout(*dims);
     const PrepLayout pl = prep_layout(dims->chains, dims->m, slots, p_max);
     const int stage_bytes = pl.ntile * PU_KB;
@@ -786,13 +800,39 @@ int bark_predict_umma(const bark_mcmc_dims* dims, const void* workspace, const v
     const unsigned char* base = (const unsigned char*)prep;
     // one persistent CTA per candidate tile loops over the samples; with fewer tiles than SMs the samples are split
     const int64_t tiles_n = ceil_div(n_c, PU_ROWS);
-    const int64_t ysplit = std::max<int64_t>(1, std::min<int64_t>(dims->chains, 148 / tiles_n));
+    const int64_t ysplit = mix ? 1 : std::max<int64_t>(1, std::min<int64_t>(dims->chains, 148 / tiles_n));
     dim3 grid((unsigned)tiles_n, (unsigned)ysplit);
     predict_umma_kernel<<<grid, PU_THREADS, sl.total, (cudaStream_t)stream>>>(
         lay, workspace, (const WalkNode*)(base + pl.off_table), base + pl.off_tiles, (const double*)(base + pl.off_scale),
-        slots, pl.kt, pl.nt, pl.ntile, ring_bytes, nb, candidates, n_c, mu, var);
+        slots, pl.kt, pl.nt, pl.ntile, ring_bytes, nb, candidates, n_c, mu, var, mix, y_mean, y_std, add_noise);
     BARK_LAUNCH_CHECK();
     return BARK_OK;
+}
+
+// per-sample moments (samples, n_c) into mu / var
+int bark_predict_umma(const bark_mcmc_dims* dims, const void* workspace, const void* prep, int32_t slots, int32_t p_max,
+                      const double* candidates, int64_t n_c, double* mu, double* var, void* stream) {
+    BARK_CHECK_ARG(dims && workspace && prep, "null pointer");
+    BARK_CHECK_ARG(n_c >= 0, "n_c < 0");
+    if (n_c == 0) return BARK_OK;
+    BARK_CHECK_ARG(candidates && mu && var, "null pointer");
+    BARK_CHECK_ARG(slots >= 1 && slots <= 255 && p_max >= 1 && p_max <= PU_MAX_P, "slots / p_max out of range");
+    BARK_CHECK_ARG(dims->chains <= 65535, "too many samples per call");
+    return predict_umma_launch(__func__, dims, workspace, prep, slots, p_max, candidates, n_c, mu, var, 0, 0.0, 1.0, 0, stream);
+}
+
+// moments (n_c) of the mixture over the samples, un-standardised (bark_predict mode 1), folded inside the kernel
+int bark_predict_umma_mixture(const bark_mcmc_dims* dims, const void* workspace, const void* prep, int32_t slots, int32_t p_max,
+                              const double* candidates, int64_t n_c, double y_mean, double y_std, int add_noise, double* mu,
+                              double* var, void* stream) {
+    BARK_CHECK_ARG(dims && workspace && prep, "null pointer");
+    BARK_CHECK_ARG(n_c >= 0, "n_c < 0");
+    if (n_c == 0) return BARK_OK;
+    BARK_CHECK_ARG(candidates && mu && var, "null pointer");
+    BARK_CHECK_ARG(slots >= 1 && slots <= 255 && p_max >= 1 && p_max <= PU_MAX_P, "slots / p_max out of range");
+    BARK_CHECK_ARG(ceil_div(n_c, PU_ROWS) <= 2147483647LL, "too many candidates per call");
+    return predict_umma_launch(__func__, dims, workspace, prep, slots, p_max, candidates, n_c, mu, var, 1, y_mean, y_std,
+                               add_noise ? 1 : 0, stream);
 }
 
 }  // extern "C"

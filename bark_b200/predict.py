@@ -23,7 +23,6 @@ class PosteriorState:
     """Per-sample leaf-space state (B^-1, w = B^-1 b, column maps) of all posterior samples, resident in HBM.
     Build once, predict many candidate batches."""
 
-    MIXTURE_CHUNK = 65536  # candidates per launch in mixture mode: 2 x S x chunk x 8 B of scratch (67 MB at S = 64)
 
     def __init__(self, model, data, feat_types, d, p_cap=None, device=None, tensor_cores=True):
         forest, noise, scale = model
@@ -98,19 +97,10 @@ class PosteriorState:
                 _lib.check(st.lib.bark_predict_umma(C.byref(st.dims), _ptr(st.ws), _ptr(self.prep), self.slots, self.p_max,
                                                     _ptr(cand_dev), n_c, _ptr(mu), _ptr(var), _stream()))
                 return mu, var
-            # mixture mode: per-sample moments only ever exist for one chunk of candidates (L2-sized scratch)
-            chunk = min(n_c, self.MIXTURE_CHUNK)
-            mu_s = torch.empty((self.num_samples, chunk), dtype=torch.float64, device=st.device)
-            var_s = torch.empty((self.num_samples, chunk), dtype=torch.float64, device=st.device)
-            for c0 in range(0, n_c, chunk):
-                nc = min(chunk, n_c - c0)
-                # (S, nc) views with row stride nc: the kernels take densely packed (S, n) outputs
-                ms, vs = mu_s.view(-1)[: self.num_samples * nc], var_s.view(-1)[: self.num_samples * nc]
-                _lib.check(st.lib.bark_predict_umma(C.byref(st.dims), _ptr(st.ws), _ptr(self.prep), self.slots, self.p_max,
-                                                    _ptr(cand_dev[c0:c0 + nc]), nc, _ptr(ms), _ptr(vs), _stream()))
-                _lib.check(st.lib.bark_predict_mixture(C.byref(st.dims), _ptr(st.ws), _ptr(ms), _ptr(vs), nc,
-                                                       float(y_mean), float(y_std), int(bool(add_noise)),
-                                                       _ptr(mu[c0:c0 + nc]), _ptr(var[c0:c0 + nc]), _stream()))
+            # mixture mode: the persistent kernel folds the samples in registers (no per-sample moments in memory)
+            _lib.check(st.lib.bark_predict_umma_mixture(C.byref(st.dims), _ptr(st.ws), _ptr(self.prep), self.slots, self.p_max,
+                                                        _ptr(cand_dev), n_c, float(y_mean), float(y_std),
+                                                        int(bool(add_noise)), _ptr(mu), _ptr(var), _stream()))
             return mu, var
         nbytes = int(st.lib.bark_predict_scratch_bytes(C.byref(st.dims), n_c))
         scratch = torch.empty(max(nbytes, 8), dtype=torch.uint8, device=st.device)

@@ -230,6 +230,11 @@ int bark_predict_prepare(const bark_mcmc_dims* dims, const void* workspace, bark
                          int32_t p_max, void* prep, void* stream);
 int bark_predict_umma(const bark_mcmc_dims* dims, const void* workspace, const void* prep, int32_t slots, int32_t p_max,
                       const double* candidates, int64_t n_c, double* mu, double* var, void* stream);
+/* The same with the mixture over the samples folded inside the kernel (one persistent CTA per 128 candidates loops over
+ * the samples): mu, var (n_c) as bark_predict mode 1 gives them, no (samples, n_c) intermediate. */
+int bark_predict_umma_mixture(const bark_mcmc_dims* dims, const void* workspace, const void* prep, int32_t slots,
+                              int32_t p_max, const double* candidates, int64_t n_c, double y_mean, double y_std,
+                              int add_noise, double* mu, double* var, void* stream);
 int bark_predict_mixture(const bark_mcmc_dims* dims, const void* workspace, const double* mu_s, const double* var_s,
                          int64_t n_c, double y_mean, double y_std, int add_noise, double* mu, double* var, void* stream);
 

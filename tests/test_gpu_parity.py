@@ -645,6 +645,35 @@ def test_predict_tensor_core_tilings(m):
     assert np.allclose(mu[:, :40], omu, rtol=1e-9, atol=1e-9) and np.allclose(var[:, :40], ovar, rtol=1e-7, atol=1e-9)
 
 
+def test_predict_mixture_folded_in_the_kernel():
+    """Mixture mode (bark_predict_umma_mixture: samples folded in registers by the persistent predict kernel) against the
+    moments formed on the host from the per-sample outputs of mode 0 with the reference's formula (bark.py:83-91), on
+    more than one wave of candidate tiles, with and without the observation noise."""
+    import torch
+    X, y, bounds, ft, _ = O.synthetic_problem(120, dim=4, cat_dim=1, num_cat=4, m_true=10, seed=5)
+    chains, m = 3, 40
+    f0 = np.tile(O.create_empty_forest(m), (chains, 1, 1))
+    p = B.BARKTrainParams(warmup_steps=10, num_samples=2, steps_per_sample=2, num_chains=chains)
+    ns, noise, scale = B.run_bark_sampler((f0, np.full(chains, 0.1), np.full(chains, 1.0)), (X, y), (bounds, ft), p, seed=3)
+    ps = B.PosteriorState((ns, noise, scale), (X, y), ft, 5)
+    assert ps.prep is not None
+    rng = np.random.default_rng(0)
+    n_c = 148 * 128 + 77
+    cand = np.hstack([rng.random((n_c, 4)), rng.integers(0, 4, size=(n_c, 1)).astype(np.float64)])
+    cd = torch.tensor(cand, device="cuda")
+    mu_s, var_s = (t.cpu().numpy() for t in ps.predict_device(cd, mode=0))
+    nz = np.asarray(noise, dtype=np.float64).reshape(-1)
+    for y_mean, y_std, add_noise in ((0.0, 1.0, False), (1.7, 0.3, True)):
+        mu, var = (t.cpu().numpy() for t in ps.predict_device(cd, mode=1, y_mean=y_mean, y_std=y_std, add_noise=add_noise))
+        mj = mu_s * y_std + y_mean
+        vj = var_s * (y_std * y_std) + (nz[:, None] if add_noise else 0.0)
+        e = mj.mean(axis=0)
+        v = (vj + mj * mj).mean(axis=0) - e * e
+        assert np.allclose(mu, e, rtol=1e-13, atol=1e-13)
+        assert np.allclose(var, v, rtol=1e-10, atol=1e-13)
+    ps.check()
+
+
 def test_tree_agreement_kernel_on_device():
     """tree_model_kernel.py:16-23 with GPU tensors in and out: equal to the oracle's forest_gram_matrix bit for bit."""
     import torch
