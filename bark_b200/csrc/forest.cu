@@ -130,14 +130,18 @@ traverse_kernel(bark_nodes_soa nodes, int64_t m, int node_limit, const double* _
     bool any_cat = false;
     for (int e = threadIdx.x; e < d; e += TRAV_THREADS) ft[e] = feat_types[e];
     for (int e = 0; e < d; ++e) any_cat |= (feat_types[e] == FEAT_CAT);  // CTA-uniform
-    // stage X tile: rows p0..p0+np are contiguous (np*d doubles) -> coalesced; store feature-major.  Numeric splits are
+    // stage X tile feature-major.  Numeric splits are
     // decided in FP32 on the candidates rounded UP: x <= (double)thr with an f32 threshold  <=>  ru_f32(x) <= thr -- the
     // reference's comparison (src/bark/forest.py:33-47) bit for bit, off the FP64 pipe.
-    for (int e = threadIdx.x; e < np * d; e += TRAV_THREADS) {
-        const int p = e / d, f = e % d;
-        const double x = X[p0 * d + e];
-        xs[(size_t)f * (TRAV_THREADS + 1) + p] = x;
-        xf[(size_t)f * (TRAV_THREADS + 1) + p] = __double2float_ru(x);
+    // (thread = point, its d features are consecutive in memory: a warp's loads cover one contiguous 32 d-double block, no
+    // integer division per element)
+    if ((int)threadIdx.x < np) {
+        const double* xr = X + (p0 + threadIdx.x) * d;
+        for (int f = 0; f < d; ++f) {
+            const double x = xr[f];
+            xs[(size_t)f * (TRAV_THREADS + 1) + threadIdx.x] = x;
+            xf[(size_t)f * (TRAV_THREADS + 1) + threadIdx.x] = __double2float_ru(x);
+        }
     }
     __syncthreads();
 
