@@ -34,7 +34,8 @@ constexpr int PU_N_MAX = 192;       // Binv columns per accumulator tile (UMMA N
                                     // columns) and two accumulators: N = 192 for K_pad <= 512, 160 above (pu_ntile)
 constexpr int PU_KB = 128;          // K bytes per operand tile (one SWIZZLE_128B atom row)
 constexpr int PU_SLICES = 7;        // base-256 digit planes
-constexpr int PU_MAX_STAGES = 8;    // ring stages; one stage = one K tile of one (column tile, digit plane)
+constexpr int PU_MAX_STAGES = 8;    // ring stages; one stage = up to PU_GROUP consecutive K tiles of one (column tile, digit plane)
+constexpr int PU_GROUP = 2;         // K tiles per stage: one bulk copy, one barrier hand-shake and one commit per group
 constexpr int PU_WALK_GROUPS = 3;   // walker threads per candidate (trees t = g mod 3)
 constexpr int PU_WALK_WARPS = 4 * PU_WALK_GROUPS;
 constexpr int PU_EPI_WARPS = 8;     // two per TMEM lane quarter: each takes half of an item's columns
@@ -53,7 +54,7 @@ __device__ __forceinline__ int pu_epilogue_half(int warp) {  // -1: not an epilo
 __device__ __forceinline__ int pu_walker_index(int warp) {  // 0 .. 11, -1: not a walker
     return (warp >= 9 && warp < 24 && (warp & 3) != 0) ? 3 * ((warp - 8) >> 2) + (warp & 3) - 1 : -1;
 }
-constexpr int PU_RING_MAX = PU_MAX_STAGES * PU_N_MAX * PU_KB;
+constexpr int PU_RING_MAX = 4 * PU_GROUP * PU_N_MAX * PU_KB;
 constexpr int PU_MAX_P = 768;
 
 __device__ __forceinline__ uint32_t pu_smem(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -347,8 +348,9 @@ predict_umma_kernel(WsLayout lay, const void* ws, const WalkNode* __restrict__ t
     uint64_t* mask_free = mask_ready + 2;            // [2] epilogue -> walkers: the sample that used the buffer is finished
     uint64_t* a_ready = mask_free + 2;               // [1] epilogue -> MMA: the A operand of the next sample is in place
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_ready + 1);
-    const int tile_bytes = ntile * PU_KB;  // one ring stage: ntile Binv columns x 128 K bytes
-    const int nstages = min(PU_MAX_STAGES, ring_bytes / tile_bytes);
+    const int tile_bytes = ntile * PU_KB;  // one K tile: ntile Binv columns x 128 K bytes
+    const int stage_bytes = PU_GROUP * tile_bytes;
+    const int nstages = min(PU_MAX_STAGES, ring_bytes / stage_bytes);
     // TMEM columns: [0, 32 kt) the one-hot A operand (row = lane, four K bytes per column), the two accumulators at the top
     const int acc_base = 512 - 2 * ntile;
     const int nwords = kt_n * 2;  // 64-column mask words per candidate row
@@ -425,12 +427,15 @@ predict_umma_kernel(WsLayout lay, const void* ws, const WalkNode* __restrict__ t
                     const int kt_lo = pu_kt_lo(nt, ntile);
                     for (int sl_ = 0; sl_ < PU_SLICES; ++sl_, src_item += (size_t)kt_n * tile_bytes) {
                         const uint8_t* src = src_item + (size_t)kt_lo * tile_bytes;
-                        for (int kt = kt_lo; kt < kt_n; ++kt, src += tile_bytes) {
+                        for (int kt = kt_lo; kt < kt_n; kt += PU_GROUP, src += (size_t)PU_GROUP * tile_bytes) {
+                            // a full group is one contiguous copy of PU_GROUP tile slots (for a narrow last column
+                            // tile the unused rows of the first slot travel along); a single tile copies its rows only
+                            const uint32_t nbytes = (kt + PU_GROUP <= kt_n) ? (uint32_t)(PU_GROUP * tile_bytes) : bytes;
                             PU_T0();
                             if (!first_lap) pu_mbar_wait(empty_bar + stage, phase, st);
                             PU_ACC(0);
-                            pu_mbar_expect_tx(full_bar + stage, bytes);
-                            pu_bulk_g2s(ring + (size_t)stage * tile_bytes, src, bytes, full_bar + stage);
+                            pu_mbar_expect_tx(full_bar + stage, nbytes);
+                            pu_bulk_g2s(ring + (size_t)stage * stage_bytes, src, nbytes, full_bar + stage);
                             PU_ACC(1);
                             if (++stage == nstages) {
                                 stage = 0;
@@ -457,7 +462,7 @@ predict_umma_kernel(WsLayout lay, const void* ws, const WalkNode* __restrict__ t
             const uint64_t desc_hi = (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);  // pu_desc_sw128 without the address
             const uint64_t b_desc0 = desc_hi | (uint64_t)((pu_smem(ring) >> 4) & 0x3FFFu);
             const uint32_t idesc_full = pu_idesc_i8(PU_ROWS, ntile), idesc_last = pu_idesc_i8(PU_ROWS, last_cols);
-            const uint32_t b_step = (uint32_t)(tile_bytes >> 4);
+            const uint32_t b_step = (uint32_t)(stage_bytes >> 4), t_step = (uint32_t)(tile_bytes >> 4);
             for (int si = 0; si < ns; ++si) {
                 unsigned* st = &chain_view(lay, const_cast<void*>(ws), s_lo + si).sc->status;
                 PU_T0();
@@ -476,18 +481,21 @@ predict_umma_kernel(WsLayout lay, const void* ws, const WalkNode* __restrict__ t
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                         const uint32_t d_addr = tmem_d + (uint32_t)acc_base + buf * (uint32_t)ntile;
                         uint32_t a_addr = tmem_d + (uint32_t)(kt_lo * (PU_KB / 4));  // 32 A columns per K tile, 8 per MMA
-                        for (int kt = kt_lo; kt < kt_n; ++kt, a_addr += PU_KB / 4) {
+                        for (int kt = kt_lo; kt < kt_n; kt += PU_GROUP) {
                             PU_T0();
                             pu_mbar_wait(full_bar + stage, full_phase, st);
                             PU_ACC(2);
                             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                            const uint64_t b_desc = b_desc0 + (uint64_t)((uint32_t)stage * b_step);
-                            pu_umma_i8_ts(d_addr, a_addr, b_desc, idesc, kt > kt_lo ? 1u : 0u);
-                            pu_umma_i8_ts(d_addr, a_addr + 8, b_desc + 2, idesc, 1u);
-                            pu_umma_i8_ts(d_addr, a_addr + 16, b_desc + 4, idesc, 1u);
-                            pu_umma_i8_ts(d_addr, a_addr + 24, b_desc + 6, idesc, 1u);
-                            // the stage of an item's last K tile is released by the epilogue when it sees acc_full
-                            if (kt + 1 < kt_n) pu_commit(empty_bar + stage);
+                            uint64_t b_desc = b_desc0 + (uint64_t)((uint32_t)stage * b_step);
+                            const int cnt = min(PU_GROUP, kt_n - kt);
+                            for (int c = 0; c < cnt; ++c, a_addr += PU_KB / 4, b_desc += t_step) {
+                                pu_umma_i8_ts(d_addr, a_addr, b_desc, idesc, (kt + c > kt_lo) ? 1u : 0u);
+                                pu_umma_i8_ts(d_addr, a_addr + 8, b_desc + 2, idesc, 1u);
+                                pu_umma_i8_ts(d_addr, a_addr + 16, b_desc + 4, idesc, 1u);
+                                pu_umma_i8_ts(d_addr, a_addr + 24, b_desc + 6, idesc, 1u);
+                            }
+                            // the stage of an item's last group is released by the epilogue when it sees acc_full
+                            if (kt + PU_GROUP < kt_n) pu_commit(empty_bar + stage);
                             PU_ACC(3);
                             if (++stage == nstages) { stage = 0; full_phase ^= 1u; }
                         }
@@ -623,7 +631,7 @@ predict_umma_kernel(WsLayout lay, const void* ws, const WalkNode* __restrict__ t
                 // the row's mask bits of this warp's columns [o, o + hcols), those beyond the tile's width cleared
                 const int o = nt * ntile + half * hcols;
                 const int valid = max(0, min(hcols, ncols - half * hcols));
-                const int item_tiles = kt_n - pu_kt_lo(nt, ntile);
+                const int item_tiles = (kt_n - pu_kt_lo(nt, ntile) + PU_GROUP - 1) / PU_GROUP;  // ring stages of the item
                 unsigned long long bits0, bits1;
                 {
                     const int wi = o >> 6, sh = o & 63;
@@ -700,7 +708,8 @@ predict_umma_kernel(WsLayout lay, const void* ws, const WalkNode* __restrict__ t
             }
             PU_T0();
             // every MMA of this sample has completed (the last acc_full): the A operand may be rewritten.  (With a single
-            // mask buffer the next sample's masks only appear after this sample's are released: build A at the end.)
+            // mask buffer the next sample's masks only appear after this sample's are released: build A at the end.
+            // Building A before the drain of the last item instead measured no gain.)
             if (nb > 1 && si + 1 < ns) build_a(si + 1);
             if (half == 1) {
 #pragma unroll
@@ -786,7 +795,7 @@ static int predict_umma_launch(const char* __func_name, const bark_mcmc_dims* di
     (void)__func_name;
     const WsLayout lay = make_layout(*dims);
     const PrepLayout pl = prep_layout(dims->chains, dims->m, slots, p_max);
-    const int stage_bytes = pl.ntile * PU_KB;
+    const int stage_bytes = PU_GROUP * pl.ntile * PU_KB;
     // two mask buffers (the walk runs a sample ahead of the MMAs) when they fit beside a ring of >= 2 stages, else one
     int nb = 2;
     size_t fixed = pu_smem_layout((int)lay.m, slots, (int)lay.d, pl.kt, 0, nb).total;
