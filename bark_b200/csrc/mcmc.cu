@@ -578,11 +578,13 @@ static cudaError_t launch_hyper(cudaStream_t st, const WsLayout& lay, void* ws, 
                                 int64_t n_sweeps, uint64_t seed, int64_t chain_offset, int64_t sweep_offset,
                                 const double* tape, double* trace, int refresh_every, cudaEvent_t mid = nullptr) {
     {
-        // forward sweep: as many CTAs per chain (1, 2 or 4) as fit on the GPU in one wave
+        // forward sweep: as many CTAs per chain (1, 2, 4 or 8) as fit on the GPU in one wave (BARK_EVAL_CLUSTER caps it)
         int dev = 0, sms = 148;
         if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        int rmax = 8;
+        if (const char* e = getenv("BARK_EVAL_CLUSTER")) rmax = std::max(1, std::min(8, atoi(e)));
         int R = 1;
-        while (R < 4 && lay.chains * (R * 2) <= sms) R *= 2;
+        while (R < rmax && lay.chains * (R * 2) <= sms) R *= 2;
         cudaLaunchConfig_t ecfg = {};
         ecfg.gridDim = dim3((unsigned)(lay.chains * R));
         ecfg.blockDim = dim3(la::THREADS);
