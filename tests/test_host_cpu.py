@@ -239,3 +239,30 @@ def test_bofire_compat_transform_and_validation():
     assert np.allclose(w, [0.25, 0.25, 0.5])  # _bark_params_to_jitclass, surrogates/bark.py:24-36
     prior = BC.surrogate_map(pm).fit(df)  # drawing from the prior is host code; no GPU needed
     assert prior.forest.shape == (5, 50, 100) and prior.train_data[0].shape == (2, 3)
+
+
+def test_predict_executed_op_count_follows_the_triangular_tiling():
+    """`PosteriorState.umma_ops_per_candidate_sample` (what bench.py divides by the measured int8 peak): 7 digit planes x
+    128-byte K tiles from the diagonal band down x column tiles of 192 (160 above 512 columns) -- csrc/predict_umma.cu
+    pu_ntile / pu_kt_lo."""
+    import types
+    from bark_b200.predict import PosteriorState
+    ops = PosteriorState.umma_ops_per_candidate_sample.fget
+
+    def by_hand(k_pad, ntile):
+        kt, total, nt = k_pad // 128, 0, 0
+        while nt * ntile < k_pad:
+            ncols = min(ntile, k_pad - nt * ntile)
+            tiles = kt - (nt * ntile) // 128
+            total += 2 * 7 * ncols * 128 * tiles
+            nt += 1
+        return total
+
+    assert ops(types.SimpleNamespace(k_pad=None)) is None
+    assert ops(types.SimpleNamespace(k_pad=128)) == 2 * 7 * 128 * 128
+    assert ops(types.SimpleNamespace(k_pad=512)) == 2 * 7 * 128 * (192 * 4 + 192 * 3 + 128 * 1) == 2637824
+    for k_pad in (256, 384, 512):
+        assert ops(types.SimpleNamespace(k_pad=k_pad)) == by_hand(k_pad, 192)
+    for k_pad in (640, 768):
+        assert ops(types.SimpleNamespace(k_pad=k_pad)) == by_hand(k_pad, 160)
+        assert ops(types.SimpleNamespace(k_pad=k_pad)) < 2 * 7 * k_pad * k_pad  # less than the full square
