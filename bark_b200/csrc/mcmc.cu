@@ -583,20 +583,42 @@ static cudaError_t launch_hyper(cudaStream_t st, const WsLayout& lay, void* ws, 
         if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         int rmax = 8;
         if (const char* e = getenv("BARK_EVAL_CLUSTER")) rmax = std::max(1, std::min(8, atoi(e)));
-        int R = 1;
-        while (R < rmax && lay.chains * (R * 2) <= sms) R *= 2;
+        // ... and every chain's cluster must be resident at once: 16 clusters of 8 do not all fit the GPCs of a B200 (a
+        // second wave doubles the step), so the driver is asked (once per chain count)
+        static int64_t cached_chains = -1;
+        static int cached_rmax = 0, cached_R = 1;
         cudaLaunchConfig_t ecfg = {};
-        ecfg.gridDim = dim3((unsigned)(lay.chains * R));
-        ecfg.blockDim = dim3(la::THREADS);
-        ecfg.dynamicSmemBytes = sizeof(la::Smem);
-        ecfg.stream = st;
         cudaLaunchAttribute eattr[1];
-        eattr[0].id = cudaLaunchAttributeClusterDimension;
-        eattr[0].val.clusterDim.x = (unsigned)R;
-        eattr[0].val.clusterDim.y = 1;
-        eattr[0].val.clusterDim.z = 1;
-        ecfg.attrs = eattr;
-        ecfg.numAttrs = 1;
+        auto configure = [&](int r) {
+            ecfg = cudaLaunchConfig_t{};
+            ecfg.gridDim = dim3((unsigned)(lay.chains * r));
+            ecfg.blockDim = dim3(la::THREADS);
+            ecfg.dynamicSmemBytes = sizeof(la::Smem);
+            ecfg.stream = st;
+            eattr[0].id = cudaLaunchAttributeClusterDimension;
+            eattr[0].val.clusterDim.x = (unsigned)r;
+            eattr[0].val.clusterDim.y = 1;
+            eattr[0].val.clusterDim.z = 1;
+            ecfg.attrs = eattr;
+            ecfg.numAttrs = 1;
+        };
+        if (cached_chains != lay.chains || cached_rmax != rmax) {
+            int R0 = 1;
+            while (R0 < rmax && lay.chains * (R0 * 2) <= sms) R0 *= 2;
+            while (R0 > 1) {
+                configure(R0);
+                int nclusters = 0;
+                const cudaError_t oe = cudaOccupancyMaxActiveClusters(&nclusters, hyper_eval_kernel, &ecfg);
+                if (oe == cudaSuccess && nclusters >= lay.chains) break;
+                if (oe != cudaSuccess) cudaGetLastError();
+                R0 /= 2;
+            }
+            cached_chains = lay.chains;
+            cached_rmax = rmax;
+            cached_R = R0;
+        }
+        const int R = cached_R;
+        configure(R);
         cudaError_t e = cudaLaunchKernelEx(&ecfg, hyper_eval_kernel, lay, ws, prm, sidx, n_sweeps, seed, chain_offset,
                                            sweep_offset, tape, trace, refresh_every);
         if (e != cudaSuccess) return e;
