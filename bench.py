@@ -160,7 +160,13 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def problem(cfg, seed=0):
+def problem(cfg, seed=0, cpu=False):
+    """The synthetic TreeFunction data set of a config.  cpu=True (the reference arm, which must not touch the GPU product
+    path) draws it with the oracle's generator: the same arrays bit for bit
+    (tests/test_gpu_parity.py::test_synthetic_generator_matches_oracle)."""
+    if cpu:
+        from oracle import bark_oracle as O
+        return O.synthetic_problem(cfg["n"], dim=cfg["d"], cat_dim=cfg["cat"], num_cat=5, m_true=50, seed=seed)
     from bark_b200 import synthetic
     return synthetic.synthetic_problem(cfg["n"], dim=cfg["d"], cat_dim=cfg["cat"], num_cat=5, m_true=50, seed=seed)
 
@@ -244,7 +250,7 @@ def run_reference_arm(a, rank, world):
         return
     if a.workload == "predict":
         cfg = CONFIGS[4]
-        X, y, bounds, ft, _ = problem(cfg)
+        X, y, bounds, ft, _ = problem(cfg, cpu=True)
         forest, noise, scale, src = reference_start_forest(cfg, 4)
         S = 64
         model = (np.tile(forest, (S, 1, 1)), np.full(S, noise), np.full(S, scale))
@@ -258,7 +264,7 @@ def run_reference_arm(a, rank, world):
         print(json.dumps(line), flush=True)
         return
     cfg = CONFIGS[a.config]
-    X, y, bounds, ft, _ = problem(cfg)
+    X, y, bounds, ft, _ = problem(cfg, cpu=True)
     forest, noise, scale, src = reference_start_forest(cfg, a.config)
     budget = max(20.0, min(150.0, 6.0 * (a.steps + a.warmup)))
     val, kind, desc, times = cpu_fit_sample(cfg, forest, noise, scale, X, y, bounds, ft, budget, steps=a.steps, warmup=a.warmup)
